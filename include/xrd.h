@@ -1,0 +1,173 @@
+/*
+ * xrd.h -- C ABI of the B200-native xritdemod sample-stream hot path.
+ *
+ * Drop-in boundary for the reference's processSamples() loop
+ * (reference demodulator/src/demodulator.cpp:100-168): decimating FIR -> AGC -> RRC FIR ->
+ * Costas loop -> Mueller&Mueller clock recovery -> complex soft symbols.  The reference has
+ * no FFI layer of its own; its "operator API" is three in-process C++ seams,
+ * and every entry point below names the seam it replaces.  Plain pointers and sizes only, no
+ * exceptions cross this boundary: functions return 0 (XRD_OK) or a negative xrd_status, and
+ * xrd_last_error() gives the message.
+ *
+ * All sample buffers are interleaved complex float (I,Q) = std::complex<float>, unless a
+ * sample `type` says otherwise (FrontendDevice.h:11-13).
+ *
+ * There is NO CPU fallback: every compute entry point runs hand-written sm_100a CUDA kernels and
+ * fails with XRD_E_CUDA when no usable device is present.
+ */
+#ifndef XRD_H_
+#define XRD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    XRD_OK = 0,
+    XRD_E_ARG = -1,      /* bad argument */
+    XRD_E_CUDA = -2,     /* CUDA runtime / launch failure, or no device */
+    XRD_E_NOMEM = -3,
+    XRD_E_OVERFLOW = -4, /* output capacity too small / FIFO overflow */
+    XRD_E_STATE = -5
+} xrd_status;
+
+/* sample types of the upstream seam: FrontendDevice.h:11-13 */
+#define XRD_FLOATIQ 0
+#define XRD_S16IQ 1
+#define XRD_S8IQ 2
+
+/* ---------------------------------------------------------------------------------------
+ * Demodulator: replaces the globals + processSamples() of demodulator.cpp:31-52,100-168
+ * ------------------------------------------------------------------------------------- */
+typedef struct xrd_demod xrd_demod;
+
+/* Field defaults (xrd_config_defaults) are the reference's Parameters.h:16-37 and the
+ * parameter derivation of demodulator.cpp:220,436-450. */
+typedef struct {
+    uint32_t sample_rate;        /* device sample rate (Hz)                                  */
+    uint32_t symbol_rate;        /* HRIT 927000 / LRIT 293883   Parameters.h:18,23           */
+    uint32_t decimation;         /* baseDecimation; 1 = decimator skipped (demodulator.cpp:136) */
+    uint32_t rrc_taps;           /* RRC_TAPS 63                                              */
+    int32_t loop_order;          /* LOOP_ORDER 2 (only 2 is implemented: BPSK)               */
+    float rrc_alpha;             /* 0.3 HRIT / 0.5 LRIT                                      */
+    float pll_alpha;             /* Costas loop bandwidth; default CLOCK_ALPHA (demodulator.cpp:220) */
+    float clock_alpha;           /* CLOCK_ALPHA 0.0037: gain_mu; gain_omega = alpha^2/4      */
+    float clock_mu;              /* CLOCK_MU 0.5                                             */
+    float clock_omega_limit;     /* CLOCK_OMEGA_LIMIT 0.005                                  */
+    float agc_rate, agc_ref, agc_gain, agc_max_gain; /* 0.01, 0.5, 1.0, 4000                 */
+    int32_t device_ordinal;      /* CUDA device                                              */
+    int32_t n_channels;          /* independent IQ streams with these parameters (>= 1)      */
+} xrd_config;
+
+/* hrit != 0: setHRITMode (demodulator.cpp:188-197); else setLRITMode (:177-186) */
+void xrd_config_defaults(xrd_config *cfg, int hrit);
+
+int xrd_create(const xrd_config *cfg, xrd_demod **out);
+void xrd_destroy(xrd_demod *d);
+const char *xrd_last_error(const xrd_demod *d); /* d may be NULL: error of the last failed create */
+
+/* == onSamplesAvailable(void *data, int length, int type)   demodulator.cpp:54-74
+ * Copies `n_complex` samples of `type` into the channel's host FIFO (capacity FIFO_SIZE,
+ * Parameters.h:57); the caller's buffer is borrowed only for the call.  Thread-safe against
+ * xrd_process.  Returns XRD_E_OVERFLOW (and drops the samples) when the FIFO is full. */
+int xrd_add_samples(xrd_demod *d, int channel, const void *data, int n_complex, int type);
+
+/* symbol sink == SymbolManager::add(std::complex<float>*, int)   SymbolManager.cpp:94-107 */
+typedef void (*xrd_symbols_cb)(void *user, int channel, const float *cf32_symbols, int n_symbols);
+
+/* == processSamples()   demodulator.cpp:100-168
+ * Runs the chain on everything queued (if at least min_samples complex samples are queued per
+ * channel; the reference's threshold is 32768, demodulator.cpp:113) and hands the symbols to
+ * `cb`.  Returns the number of complex samples consumed per channel, 0 if below threshold. */
+int64_t xrd_process(xrd_demod *d, int64_t min_samples, xrd_symbols_cb cb, void *user);
+
+/* One-shot over HOST buffers (state carried across calls, like consecutive processSamples()
+ * calls): iq holds n_channels blocks of n_complex samples of `type` (channel-major);
+ * symbols (cf32) are written to sym_out[channel * cap ...], counts to n_sym[channel].
+ * n_complex must be a multiple of the decimation (the reference silently drops the remainder,
+ * demodulator.cpp:137; here it is an error). */
+int xrd_demod_batch(xrd_demod *d, const void *iq, size_t n_complex, int type, float *sym_out, size_t cap,
+                    int64_t *n_sym);
+
+/* Same, device-resident: iq_dev / sym_dev are device pointers on cfg.device_ordinal; n_sym is a
+ * host array.  This is the call the throughput metric is quoted on. */
+int xrd_demod_device(xrd_demod *d, const void *iq_dev, size_t n_complex, int type, float *sym_dev, size_t cap,
+                     int64_t *n_sym);
+
+/* int8 soft symbols == SymbolManager::process   SymbolManager.cpp:43-46
+ * (Re(s)*127, clamp [-128,127], C cast).  Host buffers. */
+int xrd_soft_i8(xrd_demod *d, const float *sym_cf32, size_t n_symbols, int8_t *out);
+
+/* Loop state of one channel: what the five libSatHelper objects hold between Work() calls.
+ * Doubles as checkpoint (the reference never serialises it). */
+typedef struct {
+    float agc_gain;
+    float costas_phase, costas_freq;
+    float mm_mu, mm_omega;
+    float mm_p0[2], mm_p1[2];   /* interpolants of the last two symbols */
+    int64_t mm_next;            /* next interpolation base relative to the end of consumed input (<0: in retained tail) */
+    uint64_t n_in, n_sym;       /* totals since create / last set */
+} xrd_loop_state;
+int xrd_get_state(xrd_demod *d, int channel, xrd_loop_state *st);
+
+/* Segmentation of the time-parallel loops (samples); 0 keeps the default.  Results do not
+ * depend on these values -- hand-offs are certified bitwise -- only speed does. */
+typedef struct {
+    int32_t agc_seg, agc_warm;
+    int32_t costas_seg, costas_warm;
+    int64_t mm_seg, mm_warm;
+} xrd_tuning;
+int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t);
+
+/* counters since create (diagnostics; bench.py reports gpu_launches from here) */
+typedef struct {
+    uint64_t kernel_launches;
+    uint64_t agc_rounds, costas_rounds, mm_rounds;       /* fix-up rounds run */
+    uint64_t agc_redo, costas_redo, mm_redo;             /* segments re-run */
+    uint64_t mm_windows, mm_iters;                       /* fixed-point windows / iterations */
+    float ms_fir_dec, ms_agc, ms_fir_rrc, ms_costas, ms_mm;  /* device time of the last call (CUDA events) */
+} xrd_stats;
+int xrd_get_stats(xrd_demod *d, xrd_stats *s);
+
+/* ---------------------------------------------------------------------------------------
+ * Tap designers: SatHelper::Filters::RRC / lowPass   demodulator.cpp:443-444
+ * ------------------------------------------------------------------------------------- */
+/* returns the number of taps written (ntaps | 1), or < 0 */
+int xrd_design_rrc(double gain, double sample_rate, double symbol_rate, double alpha, int ntaps, float *taps, int cap);
+/* Hamming-window low-pass; returns the number of taps written, or < 0 (cap too small: -needed) */
+int xrd_design_lowpass(double gain, double sample_rate, double cutoff, double transition_width, float *taps, int cap);
+/* MMSE interpolator table of ClockRecovery: 129 rows x 8 taps */
+void xrd_mmse_table(float *table129x8);
+/* Costas loop gains from the loop bandwidth (damping sqrt(2)/2) */
+void xrd_costas_gains(float loop_bw, float *alpha, float *beta);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage operators: SatHelper::{FirFilter,AGC,CostasLoop,ClockRecovery}
+ * ctor arguments as in demodulator.cpp:446-450; work == Work(in, out, length) on HOST buffers,
+ * state carried across calls.  Each work() is one GPU stage (H2D, kernels, D2H).
+ * ------------------------------------------------------------------------------------- */
+typedef struct xrd_stage xrd_stage;
+int xrd_fir_create(int device, unsigned decimation, const float *taps, int ntaps, xrd_stage **out);
+int xrd_agc_create(int device, float rate, float reference, float gain, float max_gain, xrd_stage **out);
+int xrd_costas_create(int device, float loop_bw, int order, xrd_stage **out);
+int xrd_clock_recovery_create(int device, float omega, float gain_omega, float mu, float gain_mu,
+                              float omega_rel_limit, xrd_stage **out);
+/* FirFilter: length = OUTPUT count, consumes length*decimation inputs (demodulator.cpp:137-138).
+ * ClockRecovery: returns the number of symbols written to out (>= 0).  Others return 0. */
+int xrd_stage_work(xrd_stage *s, const float *in, float *out, int length);
+/* segmentation override for a stage (samples); 0 keeps defaults */
+int xrd_stage_set_tuning(xrd_stage *s, int64_t seg, int64_t warm);
+void xrd_stage_destroy(xrd_stage *s);
+const char *xrd_stage_last_error(const xrd_stage *s);
+
+/* library / device probe: 0 if a usable sm_100 device is present */
+int xrd_device_check(int device, char *name, int name_cap, int *sm_count, int *cc_major, int *cc_minor);
+const char *xrd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRD_H_ */

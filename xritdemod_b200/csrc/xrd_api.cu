@@ -1,0 +1,1182 @@
+// xrd_api.cu -- host side of the B200-native xritdemod hot path: stage runners, the chain
+// (processSamples(), reference demodulator/src/demodulator.cpp:100-168) and the C ABI of
+// include/xrd.h.  Compiled with -fmad=false (see xrd_kernels.cuh).
+#include "../../include/xrd.h"
+#include "xrd_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace xrd {
+
+static thread_local std::string g_create_error;
+
+struct CudaError {
+    std::string msg;
+    int code;
+};
+
+#define XRD_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            char b__[512];                                                                               \
+            snprintf(b__, sizeof b__, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            throw CudaError{b__, (e__ == cudaErrorMemoryAllocation) ? XRD_E_NOMEM : XRD_E_CUDA};          \
+        }                                                                                                \
+    } while (0)
+
+struct Counters {
+    uint64_t launches = 0;
+};
+
+#define XRD_LAUNCH(ctr, kernel, grid, block, smem, stream, ...)  \
+    do {                                                         \
+        kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);      \
+        (ctr).launches++;                                        \
+        XRD_CUDA(cudaGetLastError());                            \
+    } while (0)
+
+// grow-only device buffer (the reference's checkAndResizeBuffers, demodulator.cpp:76-92)
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t need)
+    {
+        if (need <= bytes) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        size_t want = need + need / 8 + 256;
+        XRD_CUDA(cudaMalloc(&p, want));
+        bytes = want;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    ~DevBuf()
+    {
+        if (p) cudaFree(p);
+    }
+};
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    void init()
+    {
+        if (!a) {
+            XRD_CUDA(cudaEventCreate(&a));
+            XRD_CUDA(cudaEventCreate(&b));
+        }
+    }
+    void start(cudaStream_t s) { init(); XRD_CUDA(cudaEventRecord(a, s)); }
+    void stop(cudaStream_t s) { XRD_CUDA(cudaEventRecord(b, s)); }
+    float ms()
+    {
+        float t = 0.f;
+        if (a && cudaEventSynchronize(b) == cudaSuccess) cudaEventElapsedTime(&t, a, b);
+        return t;
+    }
+    ~Timer()
+    {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// tap designers (host, FP64 then cast, as the blocks the reference names do)
+// ---------------------------------------------------------------------------------------
+static const double kPi = 3.14159265358979323846;
+
+// Filters::RRC == firdes.root_raised_cosine (demodulator.cpp:443, demod_tcp_qt.py:95-96)
+static int design_rrc(double gain, double fs, double rs, double alpha, int ntaps, std::vector<float> &out)
+{
+    ntaps |= 1;
+    out.assign(ntaps, 0.f);
+    const double spb = fs / rs;
+    const int mid = ntaps / 2;
+    double sum = 0.0;
+    for (int i = 0; i < ntaps; i++) {
+        const double xi = (double)(i - mid);
+        const double x1 = kPi * xi / spb;
+        const double x2 = 4.0 * alpha * xi / spb;
+        double x3 = x2 * x2 - 1.0;
+        double num, den;
+        if (std::fabs(x3) >= 0.000001) {
+            num = (i != mid) ? std::cos((1 + alpha) * x1) + std::sin((1 - alpha) * x1) / (4 * alpha * xi / spb)
+                             : std::cos((1 + alpha) * x1) + (1 - alpha) * kPi / (4 * alpha);
+            den = x3 * kPi;
+        } else {
+            if (alpha == 1) {
+                out[i] = -1.f;
+                sum += out[i];
+                continue;
+            }
+            const double a3 = (1 - alpha) * x1, a2 = (1 + alpha) * x1;
+            num = std::sin(a2) * (1 + alpha) * kPi - std::cos(a3) * ((1 - alpha) * kPi * spb) / (4 * alpha * xi) +
+                  std::sin(a3) * spb * spb / (4 * alpha * xi * xi);
+            den = -32 * kPi * alpha * alpha * xi / spb;
+        }
+        out[i] = (float)(4 * alpha * num / den);
+        sum += out[i];
+    }
+    for (auto &t : out) t = (float)(t * gain / sum);
+    return ntaps;
+}
+
+static int lowpass_ntaps(double fs, double tw)
+{
+    int n = (int)(53.0 * fs / (22.0 * tw));   // Hamming: 53 dB
+    return (n & 1) ? n : n + 1;
+}
+
+// Filters::lowPass(..., HAMMING) == firdes.low_pass (demodulator.cpp:444, demod_tcp_qt.py:261-262)
+static int design_lowpass(double gain, double fs, double fc, double tw, std::vector<float> &out)
+{
+    const int ntaps = lowpass_ntaps(fs, tw);
+    const int M = (ntaps - 1) / 2;
+    const double wc = 2 * kPi * fc / fs;
+    out.assign(ntaps, 0.f);
+    for (int n = -M; n <= M; n++) {
+        const float w = (float)(0.54 - 0.46 * std::cos((2 * kPi * (n + M)) / (ntaps - 1)));
+        out[n + M] = (n == 0) ? (float)(wc / kPi * w) : (float)(std::sin(n * wc) / (n * kPi) * w);
+    }
+    double fmax = out[M];
+    for (int n = 1; n <= M; n++) fmax += 2 * out[n + M];
+    const double g = gain / fmax;
+    for (auto &t : out) t = (float)(t * g);
+    return ntaps;
+}
+
+// mmse_fir_interpolator taps: least-squares 8-tap fractional delay over |f| <= 1/4, 128 steps,
+// rounded to the 6 significant digits the upstream table is printed with.  Solved here by
+// Cholesky factorisation of the (symmetric positive definite) sinc Gram matrix.
+static void mmse_table(float *tab)
+{
+    auto sinc = [](double x) { return std::fabs(x) < 1e-12 ? 1.0 : std::sin(kPi * x) / (kPi * x); };
+    const int N = MM_NTAPS;
+    const double B = 0.25;
+    double Lm[8][8] = {{0}};
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = sinc(2 * B * (double)(i - j));
+            for (int k = 0; k < j; k++) s -= Lm[i][k] * Lm[j][k];
+            Lm[i][j] = (i == j) ? std::sqrt(s) : s / Lm[j][j];
+        }
+    for (int k = 0; k <= MM_NSTEPS; k++) {
+        const double mu = (double)k / MM_NSTEPS;
+        double y[8], h[8];
+        for (int i = 0; i < N; i++) {
+            double s = sinc(2 * B * ((double)(i - 4) + mu));
+            for (int j = 0; j < i; j++) s -= Lm[i][j] * y[j];
+            y[i] = s / Lm[i][i];
+        }
+        for (int i = N - 1; i >= 0; i--) {
+            double s = y[i];
+            for (int j = i + 1; j < N; j++) s -= Lm[j][i] * h[j];
+            h[i] = s / Lm[i][i];
+        }
+        for (int j = 0; j < N; j++) {
+            char buf[64];
+            snprintf(buf, sizeof buf, "%.5e", h[j]);
+            tab[k * N + j] = (float)strtod(buf, nullptr);
+        }
+    }
+    for (int j = 0; j < N; j++) {
+        tab[j] = (j == 4) ? 1.f : 0.f;
+        tab[MM_NSTEPS * N + j] = (j == 3) ? 1.f : 0.f;
+    }
+}
+
+static void costas_gains(float bw, float &alpha, float &beta)
+{
+    // control_loop::update_gains with damping sqrt(2)/2, all FP32
+    const float damping = sqrtf(2.0f) / 2.0f;
+    const float denom = (1.0f + 2.0f * damping * bw + bw * bw);
+    alpha = (4 * damping * bw) / denom;
+    beta = (4 * bw * bw) / denom;
+}
+
+// ---------------------------------------------------------------------------------------
+// FIR stage
+// ---------------------------------------------------------------------------------------
+struct FirStage {
+    int D = 1, ntaps = 0;
+    DevBuf d_taps;
+    void init(unsigned decim, const float *taps, int n)
+    {
+        D = decim ? (int)decim : 1;
+        ntaps = n;
+        d_taps.ensure(sizeof(float) * n);
+        XRD_CUDA(cudaMemcpy(d_taps.p, taps, sizeof(float) * n, cudaMemcpyHostToDevice));
+    }
+    int hist() const { return ntaps - 1; }
+    // in: x[0] of this call (history before it); n_out outputs per channel
+    void run(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n_out, int nch, long long in_stride,
+             long long out_stride)
+    {
+        if (n_out <= 0) return;
+        const int tp = (ntaps + 1) & ~1;
+        if (D == 1) {
+            const size_t smem = sizeof(float) * tp + sizeof(float2) * (1 + FIR_TILE + ntaps - 1);
+            if (smem > 48 * 1024)
+                XRD_CUDA(cudaFuncSetAttribute(fir1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 grid((unsigned)((n_out + FIR_TILE - 1) / FIR_TILE), nch);
+            XRD_LAUNCH(c, fir1_kernel, grid, FIR_THREADS, smem, st, in, out, d_taps.as<float>(), ntaps, n_out, in_stride,
+                       out_stride);
+        } else {
+            const size_t smem = sizeof(float) * tp + sizeof(float2) * ((size_t)(FIRD_TILE - 1) * D + 1 + ntaps - 1);
+            if (smem > 48 * 1024)
+                XRD_CUDA(cudaFuncSetAttribute(fird_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 grid((unsigned)((n_out + FIRD_TILE - 1) / FIRD_TILE), nch);
+            XRD_LAUNCH(c, fird_kernel, grid, FIR_THREADS, smem, st, in, out, d_taps.as<float>(), ntaps, D, n_out,
+                       in_stride, out_stride);
+        }
+    }
+};
+
+// keep the last `keep` samples of [prefix | n] as the next call's prefix (FIR history, M&M tail)
+__global__ void carry_prefix_kernel(float2 *buf /* start of the prefix */, int keep, long long n, long long ch_stride)
+{
+    extern __shared__ float2 s_keep[];
+    buf += (size_t)blockIdx.x * ch_stride;
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) s_keep[i] = buf[n + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) buf[i] = s_keep[i];
+}
+
+template <class S> __global__ void take_last_kernel(S *carried, const S *exit_, int nseg, int nch)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < nch) carried[ch] = exit_[(size_t)ch * nseg + (nseg - 1)];
+}
+
+// ---------------------------------------------------------------------------------------
+// AGC / Costas: segment-parallel loop stage
+// ---------------------------------------------------------------------------------------
+template <class LOOP> struct SegStage {
+    typedef typename LOOP::State State;
+    typename LOOP::Params prm;
+    int L = 16384, W = 32768;
+    bool use_mirror = false;
+    int nch = 1;
+    DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo;
+    int *h_nredo = nullptr;   // pinned
+    uint64_t rounds = 0, redone = 0;
+
+    void init(int nch_, const State &s0)
+    {
+        nch = nch_;
+        d_carried.ensure(sizeof(State) * nch);
+        std::vector<State> v(nch, s0);
+        XRD_CUDA(cudaMemcpy(d_carried.p, v.data(), sizeof(State) * nch, cudaMemcpyHostToDevice));
+        d_nredo.ensure(sizeof(int));
+        if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, sizeof(int)));
+    }
+    ~SegStage()
+    {
+        if (h_nredo) cudaFreeHost(h_nredo);
+    }
+    State get(int ch)
+    {
+        State s;
+        XRD_CUDA(cudaMemcpy(&s, d_carried.as<State>() + ch, sizeof(State), cudaMemcpyDeviceToHost));
+        return s;
+    }
+
+    void run(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n, long long in_stride,
+             long long out_stride)
+    {
+        if (n <= 0) return;
+        const int nseg = (int)((n + L - 1) / L);
+        const size_t tot = (size_t)nseg * nch;
+        d_entry.ensure(sizeof(State) * tot);
+        d_exit.ensure(sizeof(State) * tot);
+        d_redo.ensure(tot);
+        if (use_mirror) d_mirror.ensure(tot);
+        const int tpb = 32;
+        dim3 grid((nseg + tpb - 1) / tpb, nch);
+        XRD_LAUNCH(c, (seg_loop_kernel<LOOP>), grid, tpb, 0, st, in, out, n, L, W, nseg, d_entry.as<State>(),
+                   d_exit.as<State>(), d_carried.as<State>(), d_redo.as<unsigned char>(), prm, 0, in_stride, out_stride);
+        for (int round = 0; nseg > 1 && round < nseg; round++) {
+            XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, sizeof(int), st));
+            XRD_LAUNCH(c, (seg_verify_kernel<LOOP>), nch, 256, 0, st, nseg, d_entry.as<State>(), d_exit.as<State>(),
+                       d_redo.as<unsigned char>(), use_mirror ? d_mirror.as<unsigned char>() : nullptr,
+                       d_nredo.as<int>(), round == 0 ? 1 : 0);
+            XRD_CUDA(cudaMemcpyAsync(h_nredo, d_nredo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            XRD_CUDA(cudaStreamSynchronize(st));
+            if (*h_nredo == 0) break;
+            rounds++;
+            redone += (uint64_t)*h_nredo;
+            XRD_LAUNCH(c, (seg_loop_kernel<LOOP>), grid, tpb, 0, st, in, out, n, L, W, nseg, d_entry.as<State>(),
+                       d_exit.as<State>(), d_carried.as<State>(), d_redo.as<unsigned char>(), prm, 1, in_stride,
+                       out_stride);
+        }
+        XRD_LAUNCH(c, (take_last_kernel<State>), (nch + 127) / 128, 128, 0, st, d_carried.as<State>(), d_exit.as<State>(),
+                   nseg, nch);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// M&M stage
+// ---------------------------------------------------------------------------------------
+__global__ void mm_rebase_kernel(MmState *carried, const MmState *exit_, int nseg, int nch, long long n)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= nch) return;
+    MmState s = exit_[(size_t)ch * nseg + (nseg - 1)];
+    s.ii -= n;   // relative to the next chunk's first sample
+    carried[ch] = s;
+}
+
+struct MmStage {
+    MmParams prm;
+    long long L = 1400000, W = 2800000;
+    int nch = 1;
+    DevBuf d_table, d_carried, d_entry, d_exit, d_redo, d_nredo, d_segout, d_offsets, d_stage, d_overflow;
+    int *h_nredo = nullptr;
+    std::vector<long long> h_offsets;
+    uint64_t rounds = 0, redone = 0, windows = 0, iters = 0;
+
+    void init(int nch_, float omega, float gain_omega, float mu, float gain_mu, float omega_rel_limit)
+    {
+        nch = nch_;
+        prm.omega_mid = omega;
+        prm.omega_lim = omega_rel_limit * omega;
+        prm.gain_omega = gain_omega;
+        prm.gain_mu = gain_mu;
+        std::vector<float> tab(129 * 8);
+        mmse_table(tab.data());
+        d_table.ensure(sizeof(float) * tab.size());
+        XRD_CUDA(cudaMemcpy(d_table.p, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice));
+        MmState s0;
+        memset(&s0, 0, sizeof s0);
+        s0.mu = mu;
+        s0.omega = omega;
+        std::vector<MmState> v(nch, s0);
+        d_carried.ensure(sizeof(MmState) * nch);
+        XRD_CUDA(cudaMemcpy(d_carried.p, v.data(), sizeof(MmState) * nch, cudaMemcpyHostToDevice));
+        d_nredo.ensure(sizeof(int));
+        d_overflow.ensure(sizeof(int));
+        if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, 2 * sizeof(int)));
+    }
+    ~MmStage()
+    {
+        if (h_nredo) cudaFreeHost(h_nredo);
+    }
+    MmState get(int ch)
+    {
+        MmState s;
+        XRD_CUDA(cudaMemcpy(&s, d_carried.as<MmState>() + ch, sizeof(MmState), cudaMemcpyDeviceToHost));
+        return s;
+    }
+    long long max_symbols(long long n) const
+    {
+        // every symbol advances the base by floor(mu + omega + gain_mu*mm) >= floor(omega_min - gain_mu)
+        double adv = std::floor((double)prm.omega_mid - (double)prm.omega_lim - (double)prm.gain_mu);
+        if (adv < 1.0) adv = 1.0;
+        return (long long)((double)(n + MM_TAIL) / adv) + 8;
+    }
+
+    // in: index 0 = first new sample (MM_TAIL samples before it addressable); out: [nch][out_cap]
+    // n_sym (host) receives per-channel counts.  Returns XRD_OK or XRD_E_OVERFLOW.
+    int run(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n, long long out_cap,
+            long long in_stride, long long out_stride, int64_t *n_sym)
+    {
+        const int nseg = (int)std::max<long long>(1, (n + L - 1) / L);
+        const size_t tot = (size_t)nseg * nch;
+        const long long cap_seg = max_symbols(std::min<long long>(L, std::max<long long>(n, 1))) + 64;
+        d_entry.ensure(sizeof(MmState) * tot);
+        d_exit.ensure(sizeof(MmState) * tot);
+        d_redo.ensure(tot);
+        d_segout.ensure(sizeof(MmSegOut) * tot);
+        d_offsets.ensure(sizeof(long long) * (size_t)(nseg + 1) * nch);
+        d_stage.ensure(sizeof(float2) * (size_t)cap_seg * tot);
+        const long long stage_stride = cap_seg * nseg;
+        dim3 grid(nseg, nch);
+        XRD_LAUNCH(c, mm_seg_kernel, grid, 32, 0, st, in, d_stage.as<float2>(), n, L, W, nseg, cap_seg,
+                   d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(), d_redo.as<unsigned char>(),
+                   d_segout.as<MmSegOut>(), d_table.as<float>(), prm, 0, in_stride, stage_stride);
+        for (int round = 0; nseg > 1 && round < nseg; round++) {
+            XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, sizeof(int), st));
+            dim3 vg((nseg + 127) / 128, nch);
+            XRD_LAUNCH(c, mm_verify_kernel, vg, 128, 0, st, nseg, d_entry.as<MmState>(), d_exit.as<MmState>(),
+                       d_redo.as<unsigned char>(), d_nredo.as<int>());
+            XRD_CUDA(cudaMemcpyAsync(h_nredo, d_nredo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            XRD_CUDA(cudaStreamSynchronize(st));
+            if (*h_nredo == 0) break;
+            rounds++;
+            redone += (uint64_t)*h_nredo;
+            XRD_LAUNCH(c, mm_seg_kernel, grid, 32, 0, st, in, d_stage.as<float2>(), n, L, W, nseg, cap_seg,
+                       d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(), d_redo.as<unsigned char>(),
+                       d_segout.as<MmSegOut>(), d_table.as<float>(), prm, 1, in_stride, stage_stride);
+        }
+        XRD_CUDA(cudaMemsetAsync(d_overflow.p, 0, sizeof(int), st));
+        XRD_LAUNCH(c, mm_offsets_kernel, nch, 32, 0, st, nseg, d_segout.as<MmSegOut>(), d_offsets.as<long long>(),
+                   d_overflow.as<int>());
+        dim3 cg(std::min(nseg, 1024), nch);
+        XRD_LAUNCH(c, mm_compact_kernel, cg, 256, 0, st, d_stage.as<float2>(), out, nseg, cap_seg,
+                   d_segout.as<MmSegOut>(), d_offsets.as<long long>(), out_cap, stage_stride, out_stride);
+        XRD_LAUNCH(c, mm_rebase_kernel, (nch + 127) / 128, 128, 0, st, d_carried.as<MmState>(), d_exit.as<MmState>(),
+                   nseg, nch, n);
+        h_offsets.resize((size_t)(nseg + 1) * nch);
+        std::vector<MmSegOut> so(tot);
+        XRD_CUDA(cudaMemcpyAsync(h_offsets.data(), d_offsets.p, sizeof(long long) * h_offsets.size(),
+                                 cudaMemcpyDeviceToHost, st));
+        XRD_CUDA(cudaMemcpyAsync(so.data(), d_segout.p, sizeof(MmSegOut) * tot, cudaMemcpyDeviceToHost, st));
+        XRD_CUDA(cudaMemcpyAsync(h_nredo + 1, d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        XRD_CUDA(cudaStreamSynchronize(st));
+        int rc = XRD_OK;
+        for (int ch = 0; ch < nch; ch++) {
+            const long long cnt = h_offsets[(size_t)ch * (nseg + 1) + nseg];
+            n_sym[ch] = cnt;
+            if (cnt > out_cap) rc = XRD_E_OVERFLOW;
+        }
+        for (auto &s : so) {
+            windows += (uint64_t)s.windows;
+            iters += (uint64_t)s.iters;
+        }
+        if (h_nredo[1]) rc = XRD_E_OVERFLOW;
+        return rc;
+    }
+};
+
+}  // namespace xrd
+
+using namespace xrd;
+
+// ---------------------------------------------------------------------------------------
+// the chain
+// ---------------------------------------------------------------------------------------
+struct HostFifo {
+    std::vector<float> buf;   // interleaved floats, ring (CircularBuffer<float>, demodulator.cpp:38)
+    size_t head = 0, count = 0;
+};
+
+struct xrd_demod {
+    xrd_config cfg;
+    std::string err;
+    int nch = 1, D = 1;
+    float sps = 0.f;
+    cudaStream_t stream = nullptr;
+    Counters ctr;
+    FirStage dec, rrc;
+    SegStage<AgcLoop> agc;
+    SegStage<CostasLoopK> costas;
+    MmStage mm;
+    // chunk buffers; per-channel stride = prefix + capacity
+    DevBuf b_in, b_dec, b_agc, b_rrc, b_cos, b_sym, b_raw, b_i8;
+    long long cap_n = 0;       // input samples per channel the buffers are sized for
+    bool hist_zeroed = false;
+    std::vector<uint64_t> n_in, n_sym;
+    Timer t_dec, t_agc, t_rrc, t_cos, t_mm;
+    float ms[5] = {0, 0, 0, 0, 0};
+    // host FIFO per channel (xrd_add_samples / xrd_process)
+    std::mutex fifo_mu;
+    std::vector<HostFifo> fifo;
+    void *h_pin = nullptr;
+    size_t h_pin_bytes = 0;
+    std::vector<float> h_sym;
+    std::vector<int64_t> h_cnt;
+
+    ~xrd_demod()
+    {
+        if (h_pin) cudaFreeHost(h_pin);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    long long in_stride() const { return cap_n + dec.hist(); }
+    long long agc_stride() const { return cap_n / D + rrc.hist(); }
+    long long cos_stride() const { return cap_n / D + MM_TAIL; }
+    long long nd_cap() const { return cap_n / D; }
+
+    void ensure(long long n)
+    {
+        if (n <= cap_n) return;
+        // carried prefixes (FIR history, M&M tail) must survive a regrow
+        const long long old_cap = cap_n;
+        const long long new_cap = n + n / 8;
+        std::vector<float2> keep_in, keep_agc, keep_cos;
+        const int Hd = (D > 1) ? dec.hist() : 0, Hr = rrc.hist();
+        if (old_cap > 0) {
+            XRD_CUDA(cudaStreamSynchronize(stream));
+            keep_in.resize((size_t)nch * Hd);
+            keep_agc.resize((size_t)nch * Hr);
+            keep_cos.resize((size_t)nch * MM_TAIL);
+            for (int ch = 0; ch < nch; ch++) {
+                if (Hd)
+                    XRD_CUDA(cudaMemcpy(keep_in.data() + (size_t)ch * Hd, b_in.as<float2>() + (size_t)ch * (old_cap + Hd),
+                                        sizeof(float2) * Hd, cudaMemcpyDeviceToHost));
+                XRD_CUDA(cudaMemcpy(keep_agc.data() + (size_t)ch * Hr,
+                                    b_agc.as<float2>() + (size_t)ch * (old_cap / D + Hr), sizeof(float2) * Hr,
+                                    cudaMemcpyDeviceToHost));
+                XRD_CUDA(cudaMemcpy(keep_cos.data() + (size_t)ch * MM_TAIL,
+                                    b_cos.as<float2>() + (size_t)ch * (old_cap / D + MM_TAIL), sizeof(float2) * MM_TAIL,
+                                    cudaMemcpyDeviceToHost));
+            }
+        }
+        cap_n = new_cap - new_cap % D;
+        const long long nd = cap_n / D;
+        if (D > 1) {
+            b_in.ensure(sizeof(float2) * (size_t)(cap_n + Hd) * nch);
+            b_dec.ensure(sizeof(float2) * (size_t)nd * nch);
+        }
+        b_agc.ensure(sizeof(float2) * (size_t)(nd + Hr) * nch);
+        b_rrc.ensure(sizeof(float2) * (size_t)nd * nch);
+        b_cos.ensure(sizeof(float2) * (size_t)(nd + MM_TAIL) * nch);
+        for (int ch = 0; ch < nch; ch++) {
+            if (Hd) {
+                float2 *p = b_in.as<float2>() + (size_t)ch * (cap_n + Hd);
+                if (old_cap > 0)
+                    XRD_CUDA(cudaMemcpy(p, keep_in.data() + (size_t)ch * Hd, sizeof(float2) * Hd, cudaMemcpyHostToDevice));
+                else
+                    XRD_CUDA(cudaMemset(p, 0, sizeof(float2) * Hd));
+            }
+            float2 *pa = b_agc.as<float2>() + (size_t)ch * (nd + Hr);
+            float2 *pc = b_cos.as<float2>() + (size_t)ch * (nd + MM_TAIL);
+            if (old_cap > 0) {
+                XRD_CUDA(cudaMemcpy(pa, keep_agc.data() + (size_t)ch * Hr, sizeof(float2) * Hr, cudaMemcpyHostToDevice));
+                XRD_CUDA(cudaMemcpy(pc, keep_cos.data() + (size_t)ch * MM_TAIL, sizeof(float2) * MM_TAIL,
+                                    cudaMemcpyHostToDevice));
+            } else {
+                XRD_CUDA(cudaMemset(pa, 0, sizeof(float2) * Hr));
+                XRD_CUDA(cudaMemset(pc, 0, sizeof(float2) * MM_TAIL));
+            }
+        }
+    }
+
+    // iq_dev: [nch][n] samples of `type` on the device.  sym_dev: [nch][cap].
+    int run_device(const void *iq_dev, long long n, int type, float2 *sym_dev, long long cap, int64_t *counts)
+    {
+        if (n % D) {
+            err = "n_complex must be a multiple of the decimation";
+            return XRD_E_ARG;
+        }
+        ensure(n);
+        const long long nd = n / D;
+        const int Hd = (D > 1) ? dec.hist() : 0, Hr = rrc.hist();
+        const float2 *x = nullptr;   // AGC input, [nch] with stride xs
+        long long xs = 0;
+        if (D > 1 || type != XRD_FLOATIQ) {
+            // ingest into b_in (behind the decimator history); D == 1 reuses b_rrc as scratch
+            float2 *dst = (D > 1) ? b_in.as<float2>() + Hd : b_rrc.as<float2>();
+            const long long ds = (D > 1) ? in_stride() : nd_cap();
+            for (int ch = 0; ch < nch; ch++) {
+                float *o = reinterpret_cast<float *>(dst + (size_t)ch * ds);
+                const size_t nf = (size_t)n * 2;
+                const int blocks = (int)std::min<size_t>((nf + 1023) / 1024, 148 * 16);
+                if (type == XRD_FLOATIQ) {
+                    XRD_CUDA(cudaMemcpyAsync(o, (const float *)iq_dev + (size_t)ch * nf, sizeof(float) * nf,
+                                             cudaMemcpyDeviceToDevice, stream));
+                } else if (type == XRD_S16IQ) {
+                    XRD_LAUNCH(ctr, (convert_kernel<short>), blocks, 256, 0, stream, (const short *)iq_dev + (size_t)ch * nf,
+                               o, nf, 1.0f / 32768.f);
+                } else {
+                    XRD_LAUNCH(ctr, (convert_kernel<signed char>), blocks, 256, 0, stream,
+                               (const signed char *)iq_dev + (size_t)ch * nf, o, nf, 1.0f / 128.f);
+                }
+            }
+            x = dst;
+            xs = ds;
+        } else {
+            x = (const float2 *)iq_dev;
+            xs = n;
+        }
+        if (D > 1) {
+            t_dec.start(stream);
+            dec.run(ctr, stream, x, b_dec.as<float2>(), nd, nch, xs, nd_cap());
+            XRD_LAUNCH(ctr, carry_prefix_kernel, nch, 256, sizeof(float2) * Hd, stream, b_in.as<float2>(), Hd, n,
+                       in_stride());
+            t_dec.stop(stream);
+            x = b_dec.as<float2>();
+            xs = nd_cap();
+        }
+        float2 *agc_out = b_agc.as<float2>() + Hr;
+        t_agc.start(stream);
+        agc.run(ctr, stream, x, agc_out, nd, xs, agc_stride());
+        t_agc.stop(stream);
+        t_rrc.start(stream);
+        // (when D == 1 and the input was converted into b_rrc, AGC has consumed it by now)
+        rrc.run(ctr, stream, agc_out, b_rrc.as<float2>(), nd, nch, agc_stride(), nd_cap());
+        XRD_LAUNCH(ctr, carry_prefix_kernel, nch, 256, sizeof(float2) * Hr, stream, b_agc.as<float2>(), Hr, nd,
+                   agc_stride());
+        t_rrc.stop(stream);
+        float2 *cos_out = b_cos.as<float2>() + MM_TAIL;
+        t_cos.start(stream);
+        costas.run(ctr, stream, b_rrc.as<float2>(), cos_out, nd, nd_cap(), cos_stride());
+        t_cos.stop(stream);
+        t_mm.start(stream);
+        int rc = mm.run(ctr, stream, cos_out, sym_dev, nd, cap, cos_stride(), cap, counts);
+        XRD_LAUNCH(ctr, carry_prefix_kernel, nch, 32, sizeof(float2) * MM_TAIL, stream, b_cos.as<float2>(), MM_TAIL, nd,
+                   cos_stride());
+        t_mm.stop(stream);
+        XRD_CUDA(cudaStreamSynchronize(stream));
+        ms[0] = (D > 1) ? t_dec.ms() : 0.f;
+        ms[1] = t_agc.ms();
+        ms[2] = t_rrc.ms();
+        ms[3] = t_cos.ms();
+        ms[4] = t_mm.ms();
+        for (int ch = 0; ch < nch; ch++) {
+            n_in[ch] += (uint64_t)n;
+            n_sym[ch] += (uint64_t)std::min<long long>(counts[ch], cap);
+        }
+        if (rc == XRD_E_OVERFLOW) err = "symbol output capacity too small";
+        return rc;
+    }
+};
+
+static size_t type_bytes(int type)
+{
+    return type == XRD_FLOATIQ ? 8 : (type == XRD_S16IQ ? 4 : (type == XRD_S8IQ ? 2 : 0));
+}
+
+template <class F> static int guarded(std::string *err, F &&f)
+{
+    try {
+        return f();
+    } catch (const CudaError &e) {
+        if (err) *err = e.msg;
+        else g_create_error = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        if (err) *err = "host allocation failed";
+        return XRD_E_NOMEM;
+    }
+}
+
+static int select_device(int dev)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return XRD_E_CUDA;
+    }
+    if (dev < 0 || dev >= n) {
+        g_create_error = "device ordinal out of range";
+        return XRD_E_ARG;
+    }
+    e = cudaSetDevice(dev);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return XRD_E_CUDA;
+    }
+    return XRD_OK;
+}
+
+extern "C" {
+
+const char *xrd_version(void) { return "xritdemod_b200 0.1 (sm_100a)"; }
+
+int xrd_device_check(int device, char *name, int name_cap, int *sm_count, int *cc_major, int *cc_minor)
+{
+    int rc = select_device(device);
+    if (rc) return rc;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return XRD_E_CUDA;
+    if (name && name_cap > 0) snprintf(name, name_cap, "%s", p.name);
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return (p.major == 10) ? XRD_OK : XRD_E_CUDA;
+}
+
+void xrd_config_defaults(xrd_config *cfg, int hrit)
+{
+    memset(cfg, 0, sizeof *cfg);
+    cfg->sample_rate = hrit ? 2500000u : 1250000u;
+    cfg->symbol_rate = hrit ? 927000u : 293883u;   // Parameters.h:18,23
+    cfg->rrc_alpha = hrit ? 0.3f : 0.5f;           // Parameters.h:19,24
+    cfg->decimation = 1;                           // DEFAULT_DECIMATION
+    cfg->rrc_taps = 63;                            // RRC_TAPS
+    cfg->loop_order = 2;                           // LOOP_ORDER
+    cfg->pll_alpha = 0.0037f;                      // demodulator.cpp:220: CLOCK_ALPHA, not PLL_ALPHA
+    cfg->clock_alpha = 0.0037f;
+    cfg->clock_mu = 0.5f;
+    cfg->clock_omega_limit = 0.005f;
+    cfg->agc_rate = 0.01f;
+    cfg->agc_ref = 0.5f;
+    cfg->agc_gain = 1.0f;
+    cfg->agc_max_gain = 4000.f;
+    cfg->device_ordinal = 0;
+    cfg->n_channels = 1;
+}
+
+int xrd_create(const xrd_config *cfg, xrd_demod **out)
+{
+    if (!cfg || !out) return XRD_E_ARG;
+    *out = nullptr;
+    if (cfg->n_channels < 1 || cfg->symbol_rate == 0 || cfg->sample_rate == 0 || cfg->rrc_taps < 1) {
+        g_create_error = "bad config";
+        return XRD_E_ARG;
+    }
+    if (cfg->loop_order != 2) {
+        g_create_error = "only loop_order 2 (BPSK) is implemented";
+        return XRD_E_ARG;
+    }
+    int rc = select_device(cfg->device_ordinal);
+    if (rc) return rc;
+    xrd_demod *d = new xrd_demod();
+    rc = guarded(nullptr, [&]() {
+        d->cfg = *cfg;
+        d->nch = cfg->n_channels;
+        d->D = cfg->decimation ? (int)cfg->decimation : 1;
+        XRD_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        // demodulator.cpp:436-437 (float arithmetic)
+        const float circuit = (float)cfg->sample_rate / (float)d->D;
+        d->sps = circuit / (float)cfg->symbol_rate;
+        std::vector<float> taps;
+        design_rrc(1, circuit, cfg->symbol_rate, cfg->rrc_alpha, (int)cfg->rrc_taps, taps);   // :443
+        d->rrc.init(1, taps.data(), (int)taps.size());                                        // :450
+        if (d->D > 1) {
+            design_lowpass(1, (double)cfg->sample_rate, circuit / 2, 100e3, taps);            // :444
+            d->dec.init(d->D, taps.data(), (int)taps.size());                                 // :446
+        }
+        d->agc.prm = AgcParams{cfg->agc_rate, cfg->agc_ref, cfg->agc_max_gain};               // :447
+        AgcState a0{cfg->agc_gain, 0.f};
+        d->agc.init(d->nch, a0);
+        float ca, cb;
+        costas_gains(cfg->pll_alpha, ca, cb);                                                 // :448
+        d->costas.prm = CostasParams{ca, cb, 1.0f, -1.0f};
+        d->costas.use_mirror = true;
+        d->costas.L = 16384;
+        d->costas.W = 24576;
+        CostasState c0{0.f, 0.f};
+        d->costas.init(d->nch, c0);
+        const float gain_omega = (cfg->clock_alpha * cfg->clock_alpha) / 4.0f;                // Parameters.h:33
+        d->mm.init(d->nch, d->sps, gain_omega, cfg->clock_mu, cfg->clock_alpha, cfg->clock_omega_limit);  // :449
+        d->n_in.assign(d->nch, 0);
+        d->n_sym.assign(d->nch, 0);
+        d->fifo.resize(d->nch);
+        return (int)XRD_OK;
+    });
+    if (rc) {
+        delete d;
+        return rc;
+    }
+    *out = d;
+    return XRD_OK;
+}
+
+void xrd_destroy(xrd_demod *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->cfg.device_ordinal);
+    delete d;
+}
+
+const char *xrd_last_error(const xrd_demod *d) { return d ? d->err.c_str() : g_create_error.c_str(); }
+
+int xrd_demod_device(xrd_demod *d, const void *iq_dev, size_t n_complex, int type, float *sym_dev, size_t cap,
+                     int64_t *n_sym)
+{
+    if (!d || !iq_dev || !sym_dev || !n_sym || !type_bytes(type)) return XRD_E_ARG;
+    return guarded(&d->err, [&]() {
+        XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
+        return d->run_device(iq_dev, (long long)n_complex, type, (float2 *)sym_dev, (long long)cap, n_sym);
+    });
+}
+
+int xrd_demod_batch(xrd_demod *d, const void *iq, size_t n_complex, int type, float *sym_out, size_t cap,
+                    int64_t *n_sym)
+{
+    if (!d || !iq || !sym_out || !n_sym || !type_bytes(type)) return XRD_E_ARG;
+    return guarded(&d->err, [&]() {
+        XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
+        const size_t in_bytes = type_bytes(type) * n_complex * d->nch;
+        d->b_raw.ensure(in_bytes);
+        d->b_sym.ensure(sizeof(float2) * cap * d->nch);
+        XRD_CUDA(cudaMemcpyAsync(d->b_raw.p, iq, in_bytes, cudaMemcpyHostToDevice, d->stream));
+        int rc = d->run_device(d->b_raw.p, (long long)n_complex, type, d->b_sym.as<float2>(), (long long)cap, n_sym);
+        if (rc != XRD_OK && rc != XRD_E_OVERFLOW) return rc;
+        for (int ch = 0; ch < d->nch; ch++) {
+            const size_t cnt = (size_t)std::min<long long>(n_sym[ch], (long long)cap);
+            XRD_CUDA(cudaMemcpyAsync(sym_out + 2 * cap * ch, d->b_sym.as<float2>() + cap * ch, sizeof(float2) * cnt,
+                                     cudaMemcpyDeviceToHost, d->stream));
+        }
+        XRD_CUDA(cudaStreamSynchronize(d->stream));
+        return rc;
+    });
+}
+
+int xrd_add_samples(xrd_demod *d, int channel, const void *data, int n_complex, int type)
+{
+    if (!d || channel < 0 || channel >= d->nch || n_complex < 0 || (!data && n_complex)) return XRD_E_ARG;
+    if (type != XRD_FLOATIQ && type != XRD_S16IQ && type != XRD_S8IQ) {
+        d->err = "Unknown sample type";   // demodulator.cpp:71-73
+        return XRD_E_ARG;
+    }
+    std::lock_guard<std::mutex> lk(d->fifo_mu);
+    HostFifo &f = d->fifo[channel];
+    const size_t FIFO = 1024 * 1024;   // FIFO_SIZE floats, Parameters.h:57
+    if (f.buf.empty()) f.buf.resize(FIFO);
+    const size_t nf = (size_t)n_complex * 2;
+    if (f.count + nf > FIFO) {
+        d->err = "Input Samples Fifo is overflowing!";   // demodulator.cpp:104-106
+        return XRD_E_OVERFLOW;
+    }
+    size_t w = (f.head + f.count) % FIFO;
+    for (size_t i = 0; i < nf; i++) {
+        float v;
+        if (type == XRD_FLOATIQ) v = ((const float *)data)[i];
+        else if (type == XRD_S16IQ) v = ((const int16_t *)data)[i] / 32768.f;   // demodulator.cpp:60-61
+        else v = ((const int8_t *)data)[i] / 128.f;                              // demodulator.cpp:67-68
+        f.buf[w] = v;
+        w = (w + 1 == FIFO) ? 0 : w + 1;
+    }
+    f.count += nf;
+    return XRD_OK;
+}
+
+int64_t xrd_process(xrd_demod *d, int64_t min_samples, xrd_symbols_cb cb, void *user)
+{
+    if (!d) return XRD_E_ARG;
+    return guarded(&d->err, [&]() -> int {
+        XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
+        const size_t FIFO = 1024 * 1024;
+        size_t n = 0;
+        {
+            std::lock_guard<std::mutex> lk(d->fifo_mu);
+            n = (size_t)-1;
+            for (auto &f : d->fifo) n = std::min(n, f.count / 2);
+            n -= n % d->D;   // keep the remainder queued (the reference drops it, demodulator.cpp:137)
+            if (n == 0 || (int64_t)n < min_samples) return 0;
+            const size_t bytes = sizeof(float) * 2 * n * d->nch;
+            if (bytes > d->h_pin_bytes) {
+                if (d->h_pin) cudaFreeHost(d->h_pin);
+                d->h_pin = nullptr;
+                XRD_CUDA(cudaMallocHost(&d->h_pin, bytes));
+                d->h_pin_bytes = bytes;
+            }
+            float *dst = (float *)d->h_pin;
+            for (int ch = 0; ch < d->nch; ch++) {
+                HostFifo &f = d->fifo[ch];
+                for (size_t i = 0; i < 2 * n; i++) {
+                    dst[(size_t)ch * 2 * n + i] = f.buf[f.head];
+                    f.head = (f.head + 1 == FIFO) ? 0 : f.head + 1;
+                }
+                f.count -= 2 * n;
+            }
+        }
+        const size_t cap = (size_t)d->mm.max_symbols((long long)(n / d->D));
+        d->h_sym.resize(2 * cap * d->nch);
+        d->h_cnt.assign(d->nch, 0);
+        int rc = xrd_demod_batch(d, d->h_pin, n, XRD_FLOATIQ, d->h_sym.data(), cap, d->h_cnt.data());
+        if (rc) return rc;
+        if (cb)
+            for (int ch = 0; ch < d->nch; ch++) cb(user, ch, d->h_sym.data() + 2 * cap * ch, (int)d->h_cnt[ch]);
+        return (int)n;
+    });
+}
+
+int xrd_soft_i8(xrd_demod *d, const float *sym, size_t n, int8_t *out)
+{
+    if (!d || (!sym && n) || (!out && n)) return XRD_E_ARG;
+    if (!n) return XRD_OK;
+    return guarded(&d->err, [&]() {
+        XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
+        d->b_sym.ensure(sizeof(float2) * n);
+        d->b_i8.ensure(n);
+        XRD_CUDA(cudaMemcpyAsync(d->b_sym.p, sym, sizeof(float2) * n, cudaMemcpyHostToDevice, d->stream));
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+        XRD_LAUNCH(d->ctr, soft_i8_kernel, blocks, 256, 0, d->stream, d->b_sym.as<float2>(), d->b_i8.as<signed char>(),
+                   (long long)n);
+        XRD_CUDA(cudaMemcpyAsync(out, d->b_i8.p, n, cudaMemcpyDeviceToHost, d->stream));
+        XRD_CUDA(cudaStreamSynchronize(d->stream));
+        return (int)XRD_OK;
+    });
+}
+
+int xrd_get_state(xrd_demod *d, int channel, xrd_loop_state *st)
+{
+    if (!d || !st || channel < 0 || channel >= d->nch) return XRD_E_ARG;
+    return guarded(&d->err, [&]() {
+        XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
+        XRD_CUDA(cudaStreamSynchronize(d->stream));
+        AgcState a = d->agc.get(channel);
+        CostasState c = d->costas.get(channel);
+        MmState m = d->mm.get(channel);
+        st->agc_gain = a.gain;
+        st->costas_phase = c.phase;
+        st->costas_freq = c.freq;
+        st->mm_mu = m.mu;
+        st->mm_omega = m.omega;
+        st->mm_p0[0] = m.p0.x;
+        st->mm_p0[1] = m.p0.y;
+        st->mm_p1[0] = m.p1.x;
+        st->mm_p1[1] = m.p1.y;
+        st->mm_next = m.ii;
+        st->n_in = d->n_in[channel];
+        st->n_sym = d->n_sym[channel];
+        return (int)XRD_OK;
+    });
+}
+
+int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
+{
+    if (!d || !t) return XRD_E_ARG;
+    if (t->agc_seg < 0 || t->agc_warm < 0 || t->costas_seg < 0 || t->costas_warm < 0 || t->mm_seg < 0 || t->mm_warm < 0)
+        return XRD_E_ARG;
+    if (t->agc_seg) d->agc.L = t->agc_seg;
+    if (t->agc_warm) d->agc.W = t->agc_warm;
+    if (t->costas_seg) d->costas.L = t->costas_seg;
+    if (t->costas_warm) d->costas.W = t->costas_warm;
+    if (t->mm_seg) d->mm.L = std::max<long long>(t->mm_seg, 64);
+    if (t->mm_warm) d->mm.W = t->mm_warm;
+    return XRD_OK;
+}
+
+int xrd_get_stats(xrd_demod *d, xrd_stats *s)
+{
+    if (!d || !s) return XRD_E_ARG;
+    memset(s, 0, sizeof *s);
+    s->kernel_launches = d->ctr.launches;
+    s->agc_rounds = d->agc.rounds;
+    s->costas_rounds = d->costas.rounds;
+    s->mm_rounds = d->mm.rounds;
+    s->agc_redo = d->agc.redone;
+    s->costas_redo = d->costas.redone;
+    s->mm_redo = d->mm.redone;
+    s->mm_windows = d->mm.windows;
+    s->mm_iters = d->mm.iters;
+    s->ms_fir_dec = d->ms[0];
+    s->ms_agc = d->ms[1];
+    s->ms_fir_rrc = d->ms[2];
+    s->ms_costas = d->ms[3];
+    s->ms_mm = d->ms[4];
+    return XRD_OK;
+}
+
+// ---- designers ----
+int xrd_design_rrc(double gain, double fs, double rs, double alpha, int ntaps, float *taps, int cap)
+{
+    if (!taps || ntaps < 1 || fs <= 0 || rs <= 0) return XRD_E_ARG;
+    std::vector<float> t;
+    int n = design_rrc(gain, fs, rs, alpha, ntaps, t);
+    if (n > cap) return -n;
+    memcpy(taps, t.data(), sizeof(float) * n);
+    return n;
+}
+
+int xrd_design_lowpass(double gain, double fs, double fc, double tw, float *taps, int cap)
+{
+    if (!taps || fs <= 0 || tw <= 0) return XRD_E_ARG;
+    std::vector<float> t;
+    int n = design_lowpass(gain, fs, fc, tw, t);
+    if (n > cap) return -n;
+    memcpy(taps, t.data(), sizeof(float) * n);
+    return n;
+}
+
+void xrd_mmse_table(float *t) { mmse_table(t); }
+void xrd_costas_gains(float bw, float *a, float *b) { costas_gains(bw, *a, *b); }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// stage operators (SatHelper::FirFilter / AGC / CostasLoop / ClockRecovery on host buffers)
+// ---------------------------------------------------------------------------------------
+struct xrd_stage {
+    enum Kind { FIR, AGC, COSTAS, MM } kind;
+    int device = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    Counters ctr;
+    FirStage fir;
+    SegStage<AgcLoop> agc;
+    SegStage<CostasLoopK> costas;
+    MmStage mm;
+    DevBuf b_in, b_out;
+    long long cap = 0;
+    int prefix = 0;
+    ~xrd_stage()
+    {
+        if (stream) cudaStreamDestroy(stream);
+    }
+    void ensure(long long n_in, long long n_out)
+    {
+        if (n_in > cap) {
+            std::vector<float2> keep(prefix);
+            if (cap > 0 && prefix) XRD_CUDA(cudaMemcpy(keep.data(), b_in.p, sizeof(float2) * prefix, cudaMemcpyDeviceToHost));
+            const bool had = cap > 0;
+            cap = n_in + n_in / 4;
+            b_in.ensure(sizeof(float2) * (size_t)(cap + prefix));
+            if (prefix) {
+                if (had) XRD_CUDA(cudaMemcpy(b_in.p, keep.data(), sizeof(float2) * prefix, cudaMemcpyHostToDevice));
+                else XRD_CUDA(cudaMemset(b_in.p, 0, sizeof(float2) * prefix));
+            }
+        }
+        b_out.ensure(sizeof(float2) * (size_t)std::max<long long>(n_out, 1));
+    }
+};
+
+static int stage_new(int device, xrd_stage::Kind k, xrd_stage **out, xrd_stage *&s)
+{
+    if (!out) return XRD_E_ARG;
+    *out = nullptr;
+    int rc = select_device(device);
+    if (rc) return rc;
+    s = new xrd_stage();
+    s->kind = k;
+    s->device = device;
+    return XRD_OK;
+}
+
+extern "C" {
+
+int xrd_fir_create(int device, unsigned decimation, const float *taps, int ntaps, xrd_stage **out)
+{
+    if (!taps || ntaps < 1) return XRD_E_ARG;
+    xrd_stage *s = nullptr;
+    int rc = stage_new(device, xrd_stage::FIR, out, s);
+    if (rc) return rc;
+    rc = guarded(nullptr, [&]() {
+        XRD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        s->fir.init(decimation, taps, ntaps);
+        s->prefix = ntaps - 1;
+        return (int)XRD_OK;
+    });
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return XRD_OK;
+}
+
+int xrd_agc_create(int device, float rate, float reference, float gain, float max_gain, xrd_stage **out)
+{
+    xrd_stage *s = nullptr;
+    int rc = stage_new(device, xrd_stage::AGC, out, s);
+    if (rc) return rc;
+    rc = guarded(nullptr, [&]() {
+        XRD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        s->agc.prm = AgcParams{rate, reference, max_gain};
+        s->agc.init(1, AgcState{gain, 0.f});
+        return (int)XRD_OK;
+    });
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return XRD_OK;
+}
+
+int xrd_costas_create(int device, float loop_bw, int order, xrd_stage **out)
+{
+    if (order != 2) {
+        g_create_error = "only order 2 (BPSK) is implemented";
+        return XRD_E_ARG;
+    }
+    xrd_stage *s = nullptr;
+    int rc = stage_new(device, xrd_stage::COSTAS, out, s);
+    if (rc) return rc;
+    rc = guarded(nullptr, [&]() {
+        XRD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        float a, b;
+        costas_gains(loop_bw, a, b);
+        s->costas.prm = CostasParams{a, b, 1.0f, -1.0f};
+        s->costas.use_mirror = true;
+        s->costas.L = 16384;
+        s->costas.W = 24576;
+        s->costas.init(1, CostasState{0.f, 0.f});
+        return (int)XRD_OK;
+    });
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return XRD_OK;
+}
+
+int xrd_clock_recovery_create(int device, float omega, float gain_omega, float mu, float gain_mu, float omega_rel_limit,
+                              xrd_stage **out)
+{
+    xrd_stage *s = nullptr;
+    int rc = stage_new(device, xrd_stage::MM, out, s);
+    if (rc) return rc;
+    rc = guarded(nullptr, [&]() {
+        XRD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        s->mm.init(1, omega, gain_omega, mu, gain_mu, omega_rel_limit);
+        s->prefix = MM_TAIL;
+        return (int)XRD_OK;
+    });
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return XRD_OK;
+}
+
+int xrd_stage_work(xrd_stage *s, const float *in, float *out, int length)
+{
+    if (!s || length < 0 || (length && (!in || !out))) return XRD_E_ARG;
+    if (length == 0) return 0;
+    return guarded(&s->err, [&]() -> int {
+        XRD_CUDA(cudaSetDevice(s->device));
+        const long long n_out = length;
+        const long long n_in = (s->kind == xrd_stage::FIR) ? n_out * s->fir.D : n_out;
+        const long long out_cap = (s->kind == xrd_stage::MM) ? s->mm.max_symbols(n_in) : n_out;
+        s->ensure(n_in, out_cap);
+        float2 *x = s->b_in.as<float2>() + s->prefix;
+        XRD_CUDA(cudaMemcpyAsync(x, in, sizeof(float2) * n_in, cudaMemcpyHostToDevice, s->stream));
+        int ret = 0;
+        long long n_copy = n_out;
+        switch (s->kind) {
+        case xrd_stage::FIR:
+            s->fir.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_out, 1, 0, 0);
+            break;
+        case xrd_stage::AGC:
+            s->agc.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_in, 0, 0);
+            break;
+        case xrd_stage::COSTAS:
+            s->costas.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_in, 0, 0);
+            break;
+        case xrd_stage::MM: {
+            int64_t cnt = 0;
+            int rc = s->mm.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_in, out_cap, 0, 0, &cnt);
+            if (rc) {
+                s->err = "symbol staging overflow";
+                return rc;
+            }
+            ret = (int)cnt;
+            n_copy = cnt;
+            break;
+        }
+        }
+        if (s->prefix)
+            XRD_LAUNCH(s->ctr, carry_prefix_kernel, 1, 256, sizeof(float2) * s->prefix, s->stream, s->b_in.as<float2>(),
+                       s->prefix, n_in, 0);
+        XRD_CUDA(cudaMemcpyAsync(out, s->b_out.p, sizeof(float2) * n_copy, cudaMemcpyDeviceToHost, s->stream));
+        XRD_CUDA(cudaStreamSynchronize(s->stream));
+        return ret;
+    });
+}
+
+int xrd_stage_set_tuning(xrd_stage *s, int64_t seg, int64_t warm)
+{
+    if (!s || seg < 0 || warm < 0) return XRD_E_ARG;
+    switch (s->kind) {
+    case xrd_stage::AGC:
+        if (seg) s->agc.L = (int)seg;
+        if (warm) s->agc.W = (int)warm;
+        break;
+    case xrd_stage::COSTAS:
+        if (seg) s->costas.L = (int)seg;
+        if (warm) s->costas.W = (int)warm;
+        break;
+    case xrd_stage::MM:
+        if (seg) s->mm.L = std::max<long long>(seg, 64);
+        if (warm) s->mm.W = warm;
+        break;
+    default:
+        break;
+    }
+    return XRD_OK;
+}
+
+void xrd_stage_destroy(xrd_stage *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    delete s;
+}
+
+const char *xrd_stage_last_error(const xrd_stage *s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+}  // extern "C"
