@@ -113,6 +113,15 @@ typedef struct {
 } xrd_loop_state;
 int xrd_get_state(xrd_demod *d, int channel, xrd_loop_state *st);
 
+/* Back to the just-created state (loop states, filter histories, queued samples, totals):
+ * what deleting and re-constructing the five operators does in the reference
+ * (demodulator.cpp:446-450, 503-523), without giving device buffers back. */
+int xrd_reset(xrd_demod *d);
+
+/* The cudaStream_t every kernel and copy of this demodulator is issued on (for callers that
+ * time with CUDA events or order their own device work against it). */
+void *xrd_stream(xrd_demod *d);
+
 /* Segmentation of the time-parallel loops (samples); 0 keeps the default.  Results do not
  * depend on these values -- hand-offs are certified bitwise -- only speed does. */
 typedef struct {

@@ -269,12 +269,18 @@ template <class LOOP> struct SegStage {
     int *h_nredo = nullptr;   // pinned
     uint64_t rounds = 0, redone = 0;
 
+    State s_init;
+    void reset()
+    {
+        std::vector<State> v(nch, s_init);
+        XRD_CUDA(cudaMemcpy(d_carried.p, v.data(), sizeof(State) * nch, cudaMemcpyHostToDevice));
+    }
     void init(int nch_, const State &s0)
     {
         nch = nch_;
+        s_init = s0;
         d_carried.ensure(sizeof(State) * nch);
-        std::vector<State> v(nch, s0);
-        XRD_CUDA(cudaMemcpy(d_carried.p, v.data(), sizeof(State) * nch, cudaMemcpyHostToDevice));
+        reset();
         d_nredo.ensure(sizeof(int));
         if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, sizeof(int)));
     }
@@ -343,6 +349,12 @@ struct MmStage {
     std::vector<long long> h_offsets;
     uint64_t rounds = 0, redone = 0, windows = 0, iters = 0;
 
+    MmState s_init;
+    void reset()
+    {
+        std::vector<MmState> v(nch, s_init);
+        XRD_CUDA(cudaMemcpy(d_carried.p, v.data(), sizeof(MmState) * nch, cudaMemcpyHostToDevice));
+    }
     void init(int nch_, float omega, float gain_omega, float mu, float gain_mu, float omega_rel_limit)
     {
         nch = nch_;
@@ -354,13 +366,11 @@ struct MmStage {
         mmse_table(tab.data());
         d_table.ensure(sizeof(float) * tab.size());
         XRD_CUDA(cudaMemcpy(d_table.p, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice));
-        MmState s0;
-        memset(&s0, 0, sizeof s0);
-        s0.mu = mu;
-        s0.omega = omega;
-        std::vector<MmState> v(nch, s0);
+        memset(&s_init, 0, sizeof s_init);
+        s_init.mu = mu;
+        s_init.omega = omega;
         d_carried.ensure(sizeof(MmState) * nch);
-        XRD_CUDA(cudaMemcpy(d_carried.p, v.data(), sizeof(MmState) * nch, cudaMemcpyHostToDevice));
+        reset();
         d_nredo.ensure(sizeof(int));
         d_overflow.ensure(sizeof(int));
         if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, 2 * sizeof(int)));
@@ -547,6 +557,27 @@ struct xrd_demod {
                 XRD_CUDA(cudaMemset(pc, 0, sizeof(float2) * MM_TAIL));
             }
         }
+    }
+
+    // back to the just-created state: loop states, FIR histories, M&M tail, counters
+    void reset()
+    {
+        XRD_CUDA(cudaStreamSynchronize(stream));
+        agc.reset();
+        costas.reset();
+        mm.reset();
+        const int Hd = (D > 1) ? dec.hist() : 0, Hr = rrc.hist();
+        if (cap_n > 0) {
+            for (int ch = 0; ch < nch; ch++) {
+                if (Hd) XRD_CUDA(cudaMemset(b_in.as<float2>() + (size_t)ch * in_stride(), 0, sizeof(float2) * Hd));
+                XRD_CUDA(cudaMemset(b_agc.as<float2>() + (size_t)ch * agc_stride(), 0, sizeof(float2) * Hr));
+                XRD_CUDA(cudaMemset(b_cos.as<float2>() + (size_t)ch * cos_stride(), 0, sizeof(float2) * MM_TAIL));
+            }
+        }
+        std::fill(n_in.begin(), n_in.end(), 0);
+        std::fill(n_sym.begin(), n_sym.end(), 0);
+        std::lock_guard<std::mutex> lk(fifo_mu);
+        for (auto &f : fifo) f.head = f.count = 0;
     }
 
     // iq_dev: [nch][n] samples of `type` on the device.  sym_dev: [nch][cap].
@@ -890,6 +921,18 @@ int xrd_soft_i8(xrd_demod *d, const float *sym, size_t n, int8_t *out)
         return (int)XRD_OK;
     });
 }
+
+int xrd_reset(xrd_demod *d)
+{
+    if (!d) return XRD_E_ARG;
+    return guarded(&d->err, [&]() {
+        XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
+        d->reset();
+        return (int)XRD_OK;
+    });
+}
+
+void *xrd_stream(xrd_demod *d) { return d ? (void *)d->stream : nullptr; }
 
 int xrd_get_state(xrd_demod *d, int channel, xrd_loop_state *st)
 {

@@ -26,7 +26,7 @@ _NP_OF_TYPE = {XRD_FLOATIQ: np.float32, XRD_S16IQ: np.int16, XRD_S8IQ: np.int8}
 # every symbol include/xrd.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "xrd_config_defaults", "xrd_create", "xrd_destroy", "xrd_last_error", "xrd_add_samples", "xrd_process",
-    "xrd_demod_batch", "xrd_demod_device", "xrd_soft_i8", "xrd_get_state", "xrd_set_tuning", "xrd_get_stats",
+    "xrd_demod_batch", "xrd_demod_device", "xrd_soft_i8", "xrd_get_state", "xrd_reset", "xrd_stream", "xrd_set_tuning", "xrd_get_stats",
     "xrd_design_rrc", "xrd_design_lowpass", "xrd_mmse_table", "xrd_costas_gains",
     "xrd_fir_create", "xrd_agc_create", "xrd_costas_create", "xrd_clock_recovery_create", "xrd_stage_work",
     "xrd_stage_set_tuning", "xrd_stage_destroy", "xrd_stage_last_error", "xrd_device_check", "xrd_version",
@@ -110,6 +110,9 @@ def lib():
     L.xrd_demod_device.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, i64p]
     L.xrd_soft_i8.argtypes = [vp, vp, C.c_size_t, vp]
     L.xrd_get_state.argtypes = [vp, C.c_int, C.POINTER(LoopState)]
+    L.xrd_reset.argtypes = [vp]
+    L.xrd_stream.argtypes = [vp]
+    L.xrd_stream.restype = vp
     L.xrd_set_tuning.argtypes = [vp, C.POINTER(Tuning)]
     L.xrd_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.xrd_design_rrc.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, C.c_int]
@@ -344,6 +347,14 @@ class Demodulator:
         st = LoopState()
         self._check(lib().xrd_get_state(self._h, channel, C.byref(st)))
         return st
+
+    def reset(self):
+        self._check(lib().xrd_reset(self._h))
+
+    @property
+    def stream(self):
+        """cudaStream_t (int) all work of this demodulator is issued on"""
+        return lib().xrd_stream(self._h) or 0
 
     def demod(self, iq, type=XRD_FLOATIQ):
         """iq: [n_channels, n] (or [n] for one channel) samples of `type`; returns a list of
