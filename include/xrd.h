@@ -128,6 +128,9 @@ typedef struct {
     int32_t agc_seg, agc_warm;
     int32_t costas_seg, costas_warm;
     int64_t mm_seg, mm_warm;
+    int32_t mm_lanes;            /* symbols per fixed-point window of the M&M chain kernel: 128/256/512/1024
+                                    (+0x10000: force the generic 64-bit kernel; tests) */
+    int32_t reserved;
 } xrd_tuning;
 int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t);
 

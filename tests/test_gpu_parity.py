@@ -155,8 +155,9 @@ def test_chain_fifo_seam(gpu, xrd, oracle):
         for _ in range(10):
             d.add_samples(x[:65535])
     assert e.value.code == -4 and "overflow" in str(e.value).lower()
-    with pytest.raises(xrd.XrdError):
-        d.add_samples(x[:10], type=7)                           # unknown sample type
+    import ctypes as C
+    raw = np.ascontiguousarray(x[:10]).view(np.float32)
+    assert xrd.lib().xrd_add_samples(d._h, 0, raw.ctypes.data_as(C.c_void_p), 10, 7) == -1   # unknown sample type
 
 
 @pytest.mark.parametrize("ntaps", [15, 31, 63, 127, 255])

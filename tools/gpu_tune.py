@@ -1,0 +1,39 @@
+"""Tuning sweep on the bench workload: stage times and fix-up counts for a list of tunings.
+usage: python tools/gpu_tune.py N_SAMPLES 'mm_lanes=512,mm_warm=1600000' 'mm_lanes=1024' ..."""
+import os, sys, time, hashlib
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from xritdemod_b200 import demod, siggen
+
+n = int(sys.argv[1])
+p = siggen.params("hrit", 0, n=n, ramp_len=1 << 20)
+h = torch.empty(2 * n, dtype=torch.float32).pin_memory()
+siggen.generate(p, n, out=h.numpy().view(np.complex64))
+x = h.cuda()
+d = demod.Demodulator(mode="hrit")
+cap = d.symbol_capacity(n)
+sym = torch.empty(2 * cap, dtype=torch.float32, device="cuda")
+ref = None
+for spec in sys.argv[2:] or [""]:
+    kw = {k: int(v) for k, v in (kv.split("=") for kv in spec.split(",") if kv)}
+    d = demod.Demodulator(mode="hrit")
+    if kw:
+        d.set_tuning(**kw)
+    best = None
+    for rep in range(int(os.environ.get("REPS", "3"))):
+        d.reset()
+        s0 = d.stats()
+        torch.cuda.synchronize(); t = time.perf_counter()
+        ns = int(d.demod_device(x.data_ptr(), n, sym.data_ptr(), cap)[0])
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t) * 1e3
+        s1 = d.stats()
+        if best is None or dt < best[0]:
+            best = (dt, s1, {k: s1[k] - s0[k] for k in s1 if k.endswith(("rounds", "redo", "iters", "launches"))})
+    digest = hashlib.sha1(sym[: 2 * ns].cpu().numpy().tobytes()).hexdigest()[:12]
+    if ref is None:
+        ref = digest
+    st = best[1]
+    print("%-40s total %8.2f ms | agc %.2f rrc %.2f costas %.2f mm %.2f | %s | nsym %d sha %s %s" % (
+        spec, best[0], st["ms_agc"], st["ms_fir_rrc"], st["ms_costas"], st["ms_mm"], best[2], ns, digest,
+        "OK" if digest == ref else "MISMATCH"), flush=True)

@@ -259,17 +259,20 @@ template <class S> __global__ void take_last_kernel(S *carried, const S *exit_, 
 // ---------------------------------------------------------------------------------------
 // AGC / Costas: segment-parallel loop stage
 // ---------------------------------------------------------------------------------------
+constexpr int SEG_NTH = 64;   // segments (threads) per CTA of the segment loop kernel
+constexpr int SEG_TS = 16;    // samples per register tile (one 128-byte line)
+
 template <class LOOP> struct SegStage {
     typedef typename LOOP::State State;
     typename LOOP::Params prm;
-    int L = 16384, W = 32768;
+    int L = 4096, W = 32768;
     bool use_mirror = false;
     int nch = 1;
-    DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo;
+    DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list;
     int *h_nredo = nullptr;   // pinned
-    uint64_t rounds = 0, redone = 0;
-
+    uint64_t rounds = 0, redone = 0, escalations = 0;
     State s_init;
+
     void reset()
     {
         std::vector<State> v(nch, s_init);
@@ -295,36 +298,59 @@ template <class LOOP> struct SegStage {
         return s;
     }
 
+    void launch(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n, int Ls, int Ws, int nseg,
+                int n_work, int mode, long long in_stride, long long out_stride)
+    {
+        const int grid = (n_work + SEG_NTH - 1) / SEG_NTH;
+        XRD_LAUNCH(c, (seg_loop_kernel<LOOP, SEG_TS>), grid, SEG_NTH, 0, st, in, out, n, Ls, Ws, nseg, n_work,
+                   d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(), prm, mode, in_stride,
+                   out_stride);
+    }
+
     void run(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n, long long in_stride,
              long long out_stride)
     {
         if (n <= 0) return;
-        const int nseg = (int)((n + L - 1) / L);
-        const size_t tot = (size_t)nseg * nch;
-        d_entry.ensure(sizeof(State) * tot);
-        d_exit.ensure(sizeof(State) * tot);
-        d_redo.ensure(tot);
-        if (use_mirror) d_mirror.ensure(tot);
-        const int tpb = 32;
-        dim3 grid((nseg + tpb - 1) / tpb, nch);
-        XRD_LAUNCH(c, (seg_loop_kernel<LOOP>), grid, tpb, 0, st, in, out, n, L, W, nseg, d_entry.as<State>(),
-                   d_exit.as<State>(), d_carried.as<State>(), d_redo.as<unsigned char>(), prm, 0, in_stride, out_stride);
-        for (int round = 0; nseg > 1 && round < nseg; round++) {
-            XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, sizeof(int), st));
-            XRD_LAUNCH(c, (seg_verify_kernel<LOOP>), nch, 256, 0, st, nseg, d_entry.as<State>(), d_exit.as<State>(),
-                       d_redo.as<unsigned char>(), use_mirror ? d_mirror.as<unsigned char>() : nullptr,
-                       d_nredo.as<int>(), round == 0 ? 1 : 0);
-            XRD_CUDA(cudaMemcpyAsync(h_nredo, d_nredo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            XRD_CUDA(cudaStreamSynchronize(st));
-            if (*h_nredo == 0) break;
-            rounds++;
-            redone += (uint64_t)*h_nredo;
-            XRD_LAUNCH(c, (seg_loop_kernel<LOOP>), grid, tpb, 0, st, in, out, n, L, W, nseg, d_entry.as<State>(),
-                       d_exit.as<State>(), d_carried.as<State>(), d_redo.as<unsigned char>(), prm, 1, in_stride,
-                       out_stride);
+        int Ls = std::max(L, SEG_TS);
+        int Ws = ((std::max(W, 0) + SEG_TS - 1) / SEG_TS) * SEG_TS;
+        for (int attempt = 0;; attempt++) {
+            const int nseg = (int)((n + Ls - 1) / Ls);
+            const size_t tot = (size_t)nseg * nch;
+            d_entry.ensure(sizeof(State) * tot);
+            d_exit.ensure(sizeof(State) * tot);
+            d_redo.ensure(tot);
+            d_list.ensure(sizeof(int) * tot);
+            if (use_mirror) d_mirror.ensure(tot);
+            launch(c, st, in, out, n, Ls, Ws, nseg, (int)tot, 0, in_stride, out_stride);
+            bool escalate = false;
+            for (int round = 0; nseg > 1 && round < nseg; round++) {
+                XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, sizeof(int), st));
+                XRD_LAUNCH(c, (seg_verify_kernel<LOOP>), nch, 256, 0, st, nseg, d_entry.as<State>(), d_exit.as<State>(),
+                           d_redo.as<unsigned char>(), use_mirror ? d_mirror.as<unsigned char>() : nullptr,
+                           d_nredo.as<int>(), d_list.as<int>(), round == 0 ? 1 : 0);
+                XRD_CUDA(cudaMemcpyAsync(h_nredo, d_nredo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                XRD_CUDA(cudaStreamSynchronize(st));
+                const int nr = *h_nredo;
+                if (nr == 0) break;
+                // speculation that mostly fails (weak signal: slow AGC; no lock) would need a fix-up round per
+                // segment: redo the pass with longer warm-ups and segments instead (bounded)
+                if (round == 0 && (size_t)nr * 100 > tot * 95 && tot >= 64 && attempt < 3) {
+                    escalate = true;
+                    break;
+                }
+                rounds++;
+                redone += (uint64_t)nr;
+                launch(c, st, in, out, n, Ls, Ws, nseg, nr, 1, in_stride, out_stride);
+            }
+            if (!escalate) {
+                XRD_LAUNCH(c, (take_last_kernel<State>), (nch + 127) / 128, 128, 0, st, d_carried.as<State>(),
+                           d_exit.as<State>(), nseg, nch);
+                return;
+            }
+            escalations++;
+            Ls *= 4;
+            Ws *= 4;
         }
-        XRD_LAUNCH(c, (take_last_kernel<State>), (nch + 127) / 128, 128, 0, st, d_carried.as<State>(), d_exit.as<State>(),
-                   nseg, nch);
     }
 };
 
@@ -340,9 +366,20 @@ __global__ void mm_rebase_kernel(MmState *carried, const MmState *exit_, int nse
     carried[ch] = s;
 }
 
+static int next_pow2(long long v)
+{
+    int r = 1;
+    while (r < v) r <<= 1;
+    return r;
+}
+
 struct MmStage {
     MmParams prm;
-    long long L = 1400000, W = 2800000;
+    long long L = 0, W = 1600000;   // L == 0: one segment per SM (set per call); W: speculative warm-up (samples)
+    long long Lmin = 262144;
+    int nt = 0;                     // lanes per chain (0 = auto)
+    bool force64 = false;           // tests: always use the generic 64-bit chain kernel
+    int sm_count = 148;
     int nch = 1;
     DevBuf d_table, d_carried, d_entry, d_exit, d_redo, d_nredo, d_segout, d_offsets, d_stage, d_overflow;
     int *h_nredo = nullptr;
@@ -374,6 +411,57 @@ struct MmStage {
         d_nredo.ensure(sizeof(int));
         d_overflow.ensure(sizeof(int));
         if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, 2 * sizeof(int)));
+        int dev = 0;
+        XRD_CUDA(cudaGetDevice(&dev));
+        XRD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // launch the chain kernel with the widest window whose sample ring fits in shared memory
+    void launch_chain(Counters &c, cudaStream_t st, dim3 grid, const float2 *in, long long n, long long Lseg, int nseg,
+                      long long cap_seg, int mode, long long in_stride, long long stage_stride)
+    {
+        const double adv = (double)prm.omega_mid + (double)prm.omega_lim + (double)prm.gain_mu + 0.01;
+        int NT = nt ? nt : 1024;
+        int R = 0;
+        for (;; NT >>= 1) {
+            // the lanes span NT * adv samples; the refill lags one iteration, so keep twice that resident
+            R = next_pow2((long long)(2 * NT * adv) + 160);
+            if (mm_chain32_smem_bytes(NT, R) <= 200 * 1024 || NT <= 128) break;
+        }
+        // the 32-bit kernel needs small per-symbol deviations (see its header comment) and 31-bit indices
+        const double dev_max = (double)NT * prm.gain_omega + prm.gain_mu;
+        const bool fast = !force64 && n < (1LL << 30) && Lseg < (1LL << 30) && W < (1LL << 30) && cap_seg < (1LL << 30) &&
+                          32.0 * dev_max < 0.45 && 2.0 * prm.omega_lim + prm.gain_mu < 0.45 && prm.omega_mid < 1024.f;
+        if (fast) {
+            const size_t smem32 = mm_chain32_smem_bytes(NT, R);
+#define XRD_MM_CHAIN32(NTV)                                                                                              \
+    do {                                                                                                                 \
+        XRD_CUDA(cudaFuncSetAttribute(mm_chain32_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32)); \
+        XRD_LAUNCH(c, mm_chain32_kernel<NTV>, grid, NTV, smem32, st, in, d_stage.as<float2>(), (int)n, (int)Lseg, (int)W, \
+                   nseg, (int)cap_seg, d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(),             \
+                   d_redo.as<unsigned char>(), d_segout.as<MmSegOut>(), d_table.as<float>(), prm, mode, in_stride,       \
+                   stage_stride, R);                                                                                     \
+    } while (0)
+            if (NT >= 1024) XRD_MM_CHAIN32(1024);
+            else if (NT == 512) XRD_MM_CHAIN32(512);
+            else if (NT == 256) XRD_MM_CHAIN32(256);
+            else XRD_MM_CHAIN32(128);
+#undef XRD_MM_CHAIN32
+            return;
+        }
+        const size_t smem = mm_chain_smem_bytes(NT, R);
+        if (smem > 227 * 1024) throw CudaError{"ClockRecovery: samples per symbol too large for the chain kernel", XRD_E_ARG};
+#define XRD_MM_CHAIN(NTV)                                                                                              \
+    do {                                                                                                               \
+        XRD_CUDA(cudaFuncSetAttribute(mm_chain_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        XRD_LAUNCH(c, mm_chain_kernel<NTV>, grid, NTV, smem, st, in, d_stage.as<float2>(), n, Lseg, W, nseg, cap_seg,  \
+                   d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(), d_redo.as<unsigned char>(),   \
+                   d_segout.as<MmSegOut>(), d_table.as<float>(), prm, mode, in_stride, stage_stride, R);               \
+    } while (0)
+        if (NT >= 1024) XRD_MM_CHAIN(1024);
+        else if (NT == 512) XRD_MM_CHAIN(512);
+        else if (NT == 256) XRD_MM_CHAIN(256);
+        else XRD_MM_CHAIN(128);
+#undef XRD_MM_CHAIN
     }
     ~MmStage()
     {
@@ -398,9 +486,15 @@ struct MmStage {
     int run(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n, long long out_cap,
             long long in_stride, long long out_stride, int64_t *n_sym)
     {
-        const int nseg = (int)std::max<long long>(1, (n + L - 1) / L);
+        // segment plan: one chain per SM unless the caller pinned a segment length
+        long long Ls = L;
+        if (Ls <= 0) {
+            const int per_ch = std::max(1, sm_count / nch);
+            Ls = std::max<long long>(Lmin, (n + per_ch - 1) / per_ch);
+        }
+        const int nseg = (int)std::max<long long>(1, (n + Ls - 1) / Ls);
         const size_t tot = (size_t)nseg * nch;
-        const long long cap_seg = max_symbols(std::min<long long>(L, std::max<long long>(n, 1))) + 64;
+        const long long cap_seg = max_symbols(std::min<long long>(Ls, std::max<long long>(n, 1))) + 64;
         d_entry.ensure(sizeof(MmState) * tot);
         d_exit.ensure(sizeof(MmState) * tot);
         d_redo.ensure(tot);
@@ -409,9 +503,7 @@ struct MmStage {
         d_stage.ensure(sizeof(float2) * (size_t)cap_seg * tot);
         const long long stage_stride = cap_seg * nseg;
         dim3 grid(nseg, nch);
-        XRD_LAUNCH(c, mm_seg_kernel, grid, 32, 0, st, in, d_stage.as<float2>(), n, L, W, nseg, cap_seg,
-                   d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(), d_redo.as<unsigned char>(),
-                   d_segout.as<MmSegOut>(), d_table.as<float>(), prm, 0, in_stride, stage_stride);
+        launch_chain(c, st, grid, in, n, Ls, nseg, cap_seg, 0, in_stride, stage_stride);
         for (int round = 0; nseg > 1 && round < nseg; round++) {
             XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, sizeof(int), st));
             dim3 vg((nseg + 127) / 128, nch);
@@ -422,9 +514,7 @@ struct MmStage {
             if (*h_nredo == 0) break;
             rounds++;
             redone += (uint64_t)*h_nredo;
-            XRD_LAUNCH(c, mm_seg_kernel, grid, 32, 0, st, in, d_stage.as<float2>(), n, L, W, nseg, cap_seg,
-                       d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(), d_redo.as<unsigned char>(),
-                       d_segout.as<MmSegOut>(), d_table.as<float>(), prm, 1, in_stride, stage_stride);
+            launch_chain(c, st, grid, in, n, Ls, nseg, cap_seg, 1, in_stride, stage_stride);
         }
         XRD_CUDA(cudaMemsetAsync(d_overflow.p, 0, sizeof(int), st));
         XRD_LAUNCH(c, mm_offsets_kernel, nch, 32, 0, st, nseg, d_segout.as<MmSegOut>(), d_offsets.as<long long>(),
@@ -586,6 +676,10 @@ struct xrd_demod {
         if (n % D) {
             err = "n_complex must be a multiple of the decimation";
             return XRD_E_ARG;
+        }
+        if (n == 0) {
+            for (int ch = 0; ch < nch; ch++) counts[ch] = 0;
+            return XRD_OK;
         }
         ensure(n);
         const long long nd = n / D;
@@ -768,14 +862,16 @@ int xrd_create(const xrd_config *cfg, xrd_demod **out)
             d->dec.init(d->D, taps.data(), (int)taps.size());                                 // :446
         }
         d->agc.prm = AgcParams{cfg->agc_rate, cfg->agc_ref, cfg->agc_max_gain};               // :447
+        d->agc.L = 2048;
+        d->agc.W = 16384;
         AgcState a0{cfg->agc_gain, 0.f};
         d->agc.init(d->nch, a0);
         float ca, cb;
         costas_gains(cfg->pll_alpha, ca, cb);                                                 // :448
         d->costas.prm = CostasParams{ca, cb, 1.0f, -1.0f};
         d->costas.use_mirror = true;
-        d->costas.L = 16384;
-        d->costas.W = 24576;
+        d->costas.L = 4096;
+        d->costas.W = 32768;
         CostasState c0{0.f, 0.f};
         d->costas.init(d->nch, c0);
         const float gain_omega = (cfg->clock_alpha * cfg->clock_alpha) / 4.0f;                // Parameters.h:33
@@ -969,6 +1065,8 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
     if (t->costas_seg) d->costas.L = t->costas_seg;
     if (t->costas_warm) d->costas.W = t->costas_warm;
     if (t->mm_seg) d->mm.L = std::max<long long>(t->mm_seg, 64);
+    if (t->mm_lanes) d->mm.nt = t->mm_lanes & 0xffff;
+    d->mm.force64 = (t->mm_lanes & 0x10000) != 0;
     if (t->mm_warm) d->mm.W = t->mm_warm;
     return XRD_OK;
 }
@@ -1096,6 +1194,8 @@ int xrd_agc_create(int device, float rate, float reference, float gain, float ma
     rc = guarded(nullptr, [&]() {
         XRD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         s->agc.prm = AgcParams{rate, reference, max_gain};
+        s->agc.L = 2048;
+        s->agc.W = 16384;
         s->agc.init(1, AgcState{gain, 0.f});
         return (int)XRD_OK;
     });
@@ -1119,8 +1219,8 @@ int xrd_costas_create(int device, float loop_bw, int order, xrd_stage **out)
         costas_gains(loop_bw, a, b);
         s->costas.prm = CostasParams{a, b, 1.0f, -1.0f};
         s->costas.use_mirror = true;
-        s->costas.L = 16384;
-        s->costas.W = 24576;
+        s->costas.L = 4096;
+        s->costas.W = 32768;
         s->costas.init(1, CostasState{0.f, 0.f});
         return (int)XRD_OK;
     });

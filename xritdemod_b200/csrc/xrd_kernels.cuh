@@ -32,6 +32,14 @@ __device__ __forceinline__ float clip_bl(float x, float c)
     return 0.5f * x1;
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS)
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // NCO sine/cosine for |x| <= 2*pi (+slack): Cody-Waite by pi/2, Cephes polynomials.
 // Operation order is part of the contract (see header comment).
 __device__ __forceinline__ void nco_sincos(float x, float &sn, float &cs)
@@ -197,14 +205,10 @@ struct AgcLoop {
     }
     __device__ static __forceinline__ bool same(const State &a, const State &b) { return a.gain == b.gain; }
     // speculative start: the gain that puts the mean level of the first samples on the reference
-    __device__ static __forceinline__ State guess(const Params &p, const float2 *in, long long begin, long long end)
+    __device__ static __forceinline__ State guess(const Params &p, const float2 *x, int m)
     {
         float acc = 0.f;
-        int m = 0;
-        for (long long i = begin; i < end && m < 32; i++, m++) {
-            const float2 v = __ldg(in + i);
-            acc += sqrtf(v.x * v.x + v.y * v.y);
-        }
+        for (int i = 0; i < m; i++) acc += sqrtf(x[i].x * x[i].x + x[i].y * x[i].y);
         State s;
         float g = (acc > 0.f) ? p.ref * (float)m / acc : 1.0f;
         if (p.max_gain > 0.0f && g > p.max_gain) g = p.max_gain;
@@ -232,9 +236,11 @@ struct CostasLoopK {
         float err = clip_bl(y.x * y.y, 1.0f);
         float freq = s.freq + p.beta * err;
         float phase = s.phase + freq + p.alpha * err;
-        while (phase > 6.283185307179586)
+        // phase_wrap compares against the double 2*pi; 0x40C90FDA < 2*pi < 0x40C90FDB, so in float
+        // "phase > 2*pi" is "phase > 6.28318500518798828125f".  The subtraction stays in double.
+        while (phase > 6.28318500518798828125f)
             phase = (float)((double)phase - 6.283185307179586);
-        while (phase < -6.283185307179586)
+        while (phase < -6.28318500518798828125f)
             phase = (float)((double)phase + 6.283185307179586);
         if (freq > p.max_freq) freq = p.max_freq;
         else if (freq < p.min_freq) freq = p.min_freq;
@@ -246,7 +252,7 @@ struct CostasLoopK {
     {
         return a.phase == b.phase && a.freq == b.freq;
     }
-    __device__ static __forceinline__ State guess(const Params &, const float2 *, long long, long long)
+    __device__ static __forceinline__ State guess(const Params &, const float2 *, int)
     {
         State s;
         s.phase = 0.f;
@@ -255,44 +261,111 @@ struct CostasLoopK {
     }
 };
 
-// mode 0: first pass -- segment j warms up over [max(0, j*L - W), j*L) from a speculative state
-//         (or from the carried exact state when the warm-up reaches the stream start), records
-//         its entry state, runs its segment writing outputs, records its exit state.
-// mode 1: fix-up pass -- segments flagged in `redo` restart at j*L from start[j] (the exact or
-//         best-known predecessor exit) and overwrite their outputs and exit state.
-template <class LOOP>
-__global__ void seg_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, int L, int W,
-                                int nseg, typename LOOP::State *__restrict__ entry,
-                                typename LOOP::State *__restrict__ exit_, const typename LOOP::State *__restrict__ carried,
-                                const unsigned char *__restrict__ redo, typename LOOP::Params prm, int mode,
-                                long long in_ch_stride, long long out_ch_stride)
+// Segment-parallel loop kernel: one thread per work item (segment).  A thread streams its own
+// samples in 128-byte tiles (TS = 16 samples = 8 x LDG.128 into registers, issued one tile ahead so
+// the HBM latency hides behind the 16 serial steps of the current tile) and writes its outputs the
+// same way (8 x STG.128): every access is a full line of a private row, the serial dependence never
+// leaves the register file, and there is no shared memory or barrier on the path.  Interior tiles
+// run a branch-free unrolled body; only tiles that straddle a stream/segment boundary take the
+// guarded path.
+//
+// mode 0: first pass -- work item w is segment g = w (g = ch * nseg + j).  Segment j warms up over
+//         [j*L - W, j*L) from a speculative state (or starts at sample 0 from the carried exact
+//         state when the warm-up would reach the stream start), records its entry state at j*L,
+//         runs its segment writing outputs, records its exit state.
+// mode 1: fix-up pass -- work item w is segment list[w]; it restarts at j*L from entry[g] (the
+//         predecessor's exit, stored there by the verify kernel) and overwrites outputs and exit.
+template <int TS> struct SegTile {
+    float2 v[TS];
+};
+
+template <int TS>
+__device__ __forceinline__ void seg_tile_load(SegTile<TS> &tl, const float2 *__restrict__ x, int s0, int lo, int len, bool vec)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ch = blockIdx.y;
-    if (j >= nseg) return;
-    in += (size_t)ch * in_ch_stride;
-    out += (size_t)ch * out_ch_stride;
-    entry += (size_t)ch * nseg;
-    exit_ += (size_t)ch * nseg;
-    const long long seg0 = (long long)j * L;
-    const long long seg1 = min(seg0 + (long long)L, n);
-    typename LOOP::State st;
-    if (mode == 0) {
-        long long begin = seg0 - W;
-        if (j == 0 || begin <= 0) {
-            begin = 0;
-            st = carried[ch];
+    if (s0 >= lo && s0 + TS <= len) {
+        if (vec) {
+            const float4 *p = reinterpret_cast<const float4 *>(x + s0);
+#pragma unroll
+            for (int i = 0; i < TS / 2; i++) {
+                const float4 q = __ldg(p + i);
+                tl.v[2 * i] = make_float2(q.x, q.y);
+                tl.v[2 * i + 1] = make_float2(q.z, q.w);
+            }
         } else {
-            st = LOOP::guess(prm, in, begin, seg0);
+#pragma unroll
+            for (int i = 0; i < TS; i++) tl.v[i] = __ldg(x + s0 + i);
         }
-        for (long long i = begin; i < seg0; i++) (void)LOOP::step(st, prm, __ldg(in + i));
-        entry[j] = st;
     } else {
-        if (!redo[(size_t)ch * nseg + j]) return;
-        st = entry[j];   // host/verify kernel stored the new start state here
+#pragma unroll
+        for (int i = 0; i < TS; i++) {
+            const int sr = s0 + i;
+            tl.v[i] = (sr >= lo && sr < len) ? __ldg(x + sr) : make_float2(0.f, 0.f);
+        }
     }
-    for (long long i = seg0; i < seg1; i++) out[i] = LOOP::step(st, prm, __ldg(in + i));
-    exit_[j] = st;
+}
+
+template <class LOOP, int TS>
+__global__ void __launch_bounds__(64)
+seg_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, int L, int W, int nseg, int n_work,
+                typename LOOP::State *__restrict__ entry, typename LOOP::State *__restrict__ exit_,
+                const typename LOOP::State *__restrict__ carried, const int *__restrict__ list,
+                typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_work) return;
+    const int g = (mode == 0) ? w : list[w];
+    const int ch = g / nseg, j = g - ch * nseg;
+    const long long seg0 = (long long)j * L;
+    const int len = (int)min((long long)L, n - seg0);
+    const int s_begin = (mode == 0) ? -W : 0;
+    // segments whose warm-up would start before the stream take the carried exact state at sample 0
+    const bool from_carried = (mode == 0) && (j == 0 || seg0 - W <= 0);
+    const int lo = (mode == 0) ? (from_carried ? (int)-seg0 : -W) : 0;
+    const float2 *x = in + (size_t)ch * in_ch_stride + seg0;
+    float2 *y = out + (size_t)ch * out_ch_stride + seg0;
+    const bool vin = ((reinterpret_cast<unsigned long long>(x) & 15) == 0);
+    const bool vout = ((reinterpret_cast<unsigned long long>(y) & 15) == 0);
+    typename LOOP::State st;
+    if (mode == 1) st = entry[g];
+    else if (from_carried) st = carried[ch];
+
+    SegTile<TS> cur, nxt;
+    seg_tile_load<TS>(cur, x, s_begin, lo, len, vin);
+    if (mode == 0 && !from_carried) st = LOOP::guess(prm, cur.v, TS);
+    for (int s0 = s_begin; s0 < L; s0 += TS) {
+        if (s0 + TS < L) seg_tile_load<TS>(nxt, x, s0 + TS, lo, len, vin);
+        if (s0 >= lo && s0 + TS <= len) {
+            // interior tile: branch-free
+            if (mode == 0 && s0 == 0) entry[g] = st;
+#pragma unroll
+            for (int e = 0; e < TS; e++) cur.v[e] = LOOP::step(st, prm, cur.v[e]);
+            if (s0 >= 0) {
+                if (vout) {
+                    float4 *p = reinterpret_cast<float4 *>(y + s0);
+#pragma unroll
+                    for (int i = 0; i < TS / 2; i++)
+                        p[i] = make_float4(cur.v[2 * i].x, cur.v[2 * i].y, cur.v[2 * i + 1].x, cur.v[2 * i + 1].y);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < TS; i++) y[s0 + i] = cur.v[i];
+                }
+            }
+        } else if (s0 + TS > lo && s0 < len) {
+            // boundary tile (unrolled as well: no dynamic indexing of the register tile)
+#pragma unroll
+            for (int e = 0; e < TS; e++) {
+                const int sr = s0 + e;
+                if (sr >= lo && sr < len) {
+                    if (mode == 0 && sr == 0) entry[g] = st;
+                    const float2 o = LOOP::step(st, prm, cur.v[e]);
+                    if (sr >= 0) y[sr] = o;
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < TS; e++) cur.v[e] = nxt.v[e];
+    }
+    exit_[g] = st;
 }
 
 // verify hand-offs: redo[j] = entry[j] != exit[j-1]; on mismatch entry[j] := exit[j-1].
@@ -304,7 +377,8 @@ __global__ void seg_loop_kernel(const float2 *__restrict__ in, float2 *__restric
 template <class LOOP>
 __global__ void seg_verify_kernel(int nseg, typename LOOP::State *__restrict__ entry,
                                   const typename LOOP::State *__restrict__ exit_, unsigned char *__restrict__ redo,
-                                  unsigned char *__restrict__ mirror, int *__restrict__ n_redo, int first_round)
+                                  unsigned char *__restrict__ mirror, int *__restrict__ n_redo, int *__restrict__ list,
+                                  int first_round)
 {
     // one CTA per channel; nseg is small (<= a few 10k): serial prefix in thread 0 for the mirror
     const int ch = blockIdx.x;
@@ -312,9 +386,6 @@ __global__ void seg_verify_kernel(int nseg, typename LOOP::State *__restrict__ e
     exit_ += (size_t)ch * nseg;
     redo += (size_t)ch * nseg;
     if (mirror) mirror += (size_t)ch * nseg;
-    __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
     if (mirror && first_round) {
         // relative rotation r_j between entry[j] and exit[j-1]; mirror[j] = xor prefix
         for (int j = threadIdx.x; j < nseg; j += blockDim.x) {
@@ -335,7 +406,6 @@ __global__ void seg_verify_kernel(int nseg, typename LOOP::State *__restrict__ e
         }
         __syncthreads();
     }
-    int cnt = 0;
     for (int j = threadIdx.x; j < nseg; j += blockDim.x) {
         unsigned char r = 0;
         if (j > 0) {
@@ -351,16 +421,13 @@ __global__ void seg_verify_kernel(int nseg, typename LOOP::State *__restrict__ e
             }
         }
         redo[j] = r;
-        cnt += r;
+        if (r) list[atomicAdd(n_redo, 1)] = ch * nseg + j;   // work list of the fix-up pass
     }
     __syncthreads();
     if (mirror) {
         // after this round every segment either matched a de-rotated state or is re-run from one
         for (int j = threadIdx.x; j < nseg; j += blockDim.x) mirror[j] = 0;
     }
-    if (cnt) atomicAdd(&s_cnt, cnt);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_cnt) atomicAdd(n_redo, s_cnt);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -611,6 +678,573 @@ mm_seg_kernel(const float2 *__restrict__ in /* index 0 = first new sample; MM_TA
         so.overflow = overflow;
         so.iters = iters;
         so.windows = windows;
+        segout[j] = so;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// M&M as a CTA-wide sliding-window chain: one CTA per segment, NT lanes = NT consecutive symbols.
+//
+// Same fixed point as above, but the window slides: symbol s lives in lane s mod NT (a ring), every
+// iteration all NT lanes apply the literal transition to their believed states, the increments are
+// prefix-summed in symbol order from the exact base lane, and the leading run of lanes whose
+// believed state did not change is exact and is emitted (lane r's new state is exact when lanes
+// 0..r-1 were).  The freed lanes re-enter at the far end with linearly extrapolated states, so
+// every lane has been refined several times by the time the exact front reaches it: the front
+// advances ~200 symbols per iteration at NT = 1024 (tools/emul/mm_window_emul.c) instead of one
+// symbol per ~150 cycles of a serial thread.  Samples are staged in a shared-memory ring filled by
+// cp.async ahead of the lanes.
+// ---------------------------------------------------------------------------------------
+
+constexpr int MM_TAB_PAD = 1040;   // 8 * 129 floats, padded
+
+__host__ __device__ inline size_t mm_chain_smem_bytes(int NT, int R)
+{
+    return sizeof(float) * MM_TAB_PAD + sizeof(float2) * NT + sizeof(long long) * (32 + 32 + 8) + sizeof(unsigned) * 8 +
+           sizeof(float2) * (size_t)R;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+mm_chain_kernel(const float2 *__restrict__ in /* index 0 = first new sample; MM_TAIL before it valid */,
+                float2 *__restrict__ stage, long long n, long long L, long long W, int nseg, long long cap_seg,
+                MmState *__restrict__ entry, MmState *__restrict__ exit_, const MmState *__restrict__ carried,
+                const unsigned char *__restrict__ redo, MmSegOut *__restrict__ segout, const float *__restrict__ table,
+                MmParams prm, int mode, long long in_ch_stride, long long stage_ch_stride, int R)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float *s_tab = reinterpret_cast<float *>(s_raw);
+    float2 *s_p = reinterpret_cast<float2 *>(s_tab + MM_TAB_PAD);
+    long long *s_wT = reinterpret_cast<long long *>(s_p + NT);
+    long long *s_wW = s_wT + 32;
+    long long *s_misc = s_wW + 32;   // 0,1: within-warp exclusive of the base lane; 2,3: new base; 4,5: end state; 6,7: totals
+    unsigned *s_min = reinterpret_cast<unsigned *>(s_misc + 8);   // [parity*4 + {first changed, stop, entry}]
+    float2 *s_x = reinterpret_cast<float2 *>(s_min + 8);
+    constexpr int NW = NT / 32;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int j = blockIdx.x, ch = blockIdx.y;
+    in += (size_t)ch * in_ch_stride;
+    stage += (size_t)ch * stage_ch_stride + (size_t)j * cap_seg;
+    entry += (size_t)ch * nseg;
+    exit_ += (size_t)ch * nseg;
+    segout += (size_t)ch * nseg;
+    if (mode == 1 && !redo[(size_t)ch * nseg + j]) return;
+    for (int i = t; i < 129 * 8; i += NT) {
+        const int k = i >> 3, tp = i & 7;
+        s_tab[tp * 129 + k] = table[i];
+    }
+    if (t < 8) s_min[t] = NT;
+
+    const long long seg0 = (j == 0) ? -(1LL << 62) : (long long)j * L;
+    const long long seg1 = (j == nseg - 1) ? (1LL << 62) : (long long)(j + 1) * L;
+    const long long last_ok = n - MM_NTAPS;
+    MmState st;
+    bool have_entry;
+    if (mode == 0) {
+        const long long begin = (long long)j * L - W;
+        if (j == 0 || begin <= 0) {
+            st = carried[ch];
+        } else {
+            st.ii = begin;
+            st.mu = 0.5f;
+            st.omega = prm.omega_mid;
+            st.p0 = make_float2(0.f, 0.f);
+            st.p1 = make_float2(0.f, 0.f);
+        }
+        have_entry = false;
+    } else {
+        st = entry[j];
+        have_entry = true;
+    }
+    long long Tb = st.ii * 4294967296LL + (long long)(st.mu * MM_FIX);
+    long long Wb = (long long)(st.omega * MM_FIX);
+    float2 P1 = st.p0, P2 = st.p1;
+    int tb = 0, count = 0, overflow = 0, iters = 0, par = 0;
+    // believed state of this lane: linear extrapolation with zero timing error
+    long long T = Tb + (long long)t * Wb, Wv = Wb;
+    long long c_ii = -(1LL << 62);
+    int c_k = -1;
+    float2 p0 = make_float2(0.f, 0.f);
+    const int RM = R - 1;
+    const long long lo_min = -(long long)MM_TAIL;
+    // ring: sample i sits in s_x[i & RM]; samples [x_fill - R, x_fill) are resident
+    long long x_fill = ((st.ii < lo_min ? lo_min : st.ii) & ~31LL);
+    {
+        const long long target = x_fill + R;
+        for (long long i = x_fill + t; i < target; i += NT)
+            if (i >= lo_min && i < n) cp_async8(&s_x[i & RM], in + i);
+        x_fill = target;
+    }
+
+    for (;;) {
+        iters++;
+        cp_async_wait_all();
+        __syncthreads();   // S0: ring visible, previous iteration's shared scratch consumed
+        // ---- 1. interpolate at the believed state (skipped when (ii, k) did not move)
+        const long long ii = T >> 32;
+        const unsigned lo32 = (unsigned)(T & 0xffffffffLL);
+        const float mu = (float)lo32 * MM_UNFIX;
+        const float om = (float)Wv * MM_UNFIX;
+        const int k = (int)rintf(mu * (float)MM_NSTEPS);
+        const bool inrange = (ii >= x_fill - R) && (ii >= lo_min) && (ii + MM_NTAPS <= x_fill) && (ii <= last_ok);
+        if (!inrange) {
+            p0 = make_float2(0.f, 0.f);
+            c_k = -1;   // never trust a cached interpolant across an out-of-ring visit
+        } else if (ii != c_ii || k != c_k) {
+            c_ii = ii;
+            c_k = k;
+            {
+                const int b = (int)(ii & RM);
+                float ar[4], ai[4];
+#pragma unroll
+                for (int l = 0; l < 4; l++) {
+                    const float t0 = s_tab[(7 - l) * 129 + k];
+                    const float t1 = s_tab[(3 - l) * 129 + k];
+                    const float2 a = s_x[(b + l) & RM], bb = s_x[(b + l + 4) & RM];
+                    ar[l] = fmaf(t1, bb.x, t0 * a.x);
+                    ai[l] = fmaf(t1, bb.y, t0 * a.y);
+                }
+                p0 = make_float2((ar[0] + ar[1]) + (ar[2] + ar[3]), (ai[0] + ai[1]) + (ai[2] + ai[3]));
+            }
+        }
+        s_p[t] = p0;
+        __syncthreads();   // S1
+        // ---- 2. literal loop update with the two preceding symbols' interpolants
+        const int r = (t - tb) & (NT - 1);
+        float2 p1 = s_p[(t - 1) & (NT - 1)], p2 = s_p[(t - 2) & (NT - 1)];
+        if (r == 0) { p1 = P1; p2 = P2; }
+        if (r == 1) { p2 = P1; }
+        float mu2 = mu, om2 = om;
+        long long ii2 = ii;
+        mm_update(prm, p0, p1, p2, mu2, om2, ii2);
+        const long long dT = (ii2 - ii) * 4294967296LL + ((long long)(mu2 * MM_FIX) - (long long)lo32);
+        const long long dW = (long long)(om2 * MM_FIX) - Wv;
+        // ---- 3. inclusive scan in thread order
+        long long iT = dT, iW = dW;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long a = __shfl_up_sync(0xffffffffu, iT, o);
+            const long long b = __shfl_up_sync(0xffffffffu, iW, o);
+            if (lane >= o) { iT += a; iW += b; }
+        }
+        if (lane == 31) { s_wT[wid] = iT; s_wW[wid] = iW; }
+        if (t == tb) { s_misc[0] = iT - dT; s_misc[1] = iW - dW; }
+        __syncthreads();   // S2
+        if (wid == 0) {
+            long long a = (lane < NW) ? s_wT[lane] : 0, b = (lane < NW) ? s_wW[lane] : 0;
+            const long long a0 = a, b0 = b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long x = __shfl_up_sync(0xffffffffu, a, o);
+                const long long y = __shfl_up_sync(0xffffffffu, b, o);
+                if (lane >= o) { a += x; b += y; }
+            }
+            if (lane < NW) { s_wT[lane] = a - a0; s_wW[lane] = b - b0; }
+            if (lane == 31) { s_misc[6] = a; s_misc[7] = b; }
+        }
+        __syncthreads();   // S3
+        // ---- 4. states implied by the increments, in symbol order from the base lane
+        const long long eT = s_wT[wid] + (iT - dT), eW = s_wW[wid] + (iW - dW);
+        const long long bT = s_wT[tb >> 5] + s_misc[0], bW = s_wW[tb >> 5] + s_misc[1];
+        const long long rotT = (t >= tb) ? eT - bT : s_misc[6] - bT + eT;
+        const long long rotW = (t >= tb) ? eW - bW : s_misc[7] - bW + eW;
+        const long long nT = Tb + rotT, nW = Wb + rotW;
+        const long long nii = nT >> 32;
+        const bool changed = (nT != T) || (nW != Wv) || !inrange;
+        const bool stopc = (nii > last_ok) || (nii >= seg1);
+        const bool entc = !have_entry && (nii >= seg0);
+        unsigned m0 = __reduce_min_sync(0xffffffffu, changed ? (unsigned)r : (unsigned)NT);
+        unsigned m1 = __reduce_min_sync(0xffffffffu, stopc ? (unsigned)r : (unsigned)NT);
+        unsigned m2 = __reduce_min_sync(0xffffffffu, entc ? (unsigned)r : (unsigned)NT);
+        if (lane == 0) {
+            if (m0 < NT) atomicMin(&s_min[par * 4 + 0], m0);
+            if (m1 < NT) atomicMin(&s_min[par * 4 + 1], m1);
+            if (m2 < NT) atomicMin(&s_min[par * 4 + 2], m2);
+        }
+        __syncthreads();   // S4
+        const int A = (int)s_min[par * 4 + 0];        // lanes r < A hold exact states and interpolants; lane A's new state is exact
+        const int r_stop = (int)s_min[par * 4 + 1];
+        int r_ent = (int)s_min[par * 4 + 2];
+        const bool stop = (r_stop < NT) && (r_stop <= A);
+        const int hi = stop ? r_stop : A;             // symbols r < hi are final
+        int lo = 0;
+        if (!have_entry) {
+            if (r_ent > r_stop) r_ent = r_stop;       // empty segment: the stop lane is also the entry
+            if (r_ent <= hi && r_ent < NT) {
+                lo = r_ent;
+                if (r == r_ent) {
+                    float2 q1 = s_p[(t - 1) & (NT - 1)], q2 = s_p[(t - 2) & (NT - 1)];
+                    if (r == 0) { q1 = P1; q2 = P2; }
+                    if (r == 1) { q2 = P1; }
+                    MmState s;
+                    s.ii = nii;
+                    s.mu = (float)(unsigned)(nT & 0xffffffffLL) * MM_UNFIX;
+                    s.omega = (float)nW * MM_UNFIX;
+                    s.p0 = q1;
+                    s.p1 = q2;
+                    entry[j] = s;
+                }
+                have_entry = true;
+            } else {
+                lo = hi;   // still warming up: nothing to emit
+            }
+        }
+        if (r >= lo && r < hi) {
+            const long long pos = (long long)count + (r - lo);
+            if (pos < cap_seg) stage[pos] = p0;
+            else overflow = 1;
+        }
+        count += (hi > lo) ? (hi - lo) : 0;
+        if (stop) {
+            if (r == r_stop) {
+                float2 q1 = s_p[(t - 1) & (NT - 1)], q2 = s_p[(t - 2) & (NT - 1)];
+                if (r == 0) { q1 = P1; q2 = P2; }
+                if (r == 1) { q2 = P1; }
+                MmState s;
+                s.ii = nii;
+                s.mu = (float)(unsigned)(nT & 0xffffffffLL) * MM_UNFIX;
+                s.omega = (float)nW * MM_UNFIX;
+                s.p0 = q1;
+                s.p1 = q2;
+                exit_[j] = s;
+            }
+            break;
+        }
+        // ---- 5. slide: the base moves to lane A, freed lanes re-enter at the far end
+        if (A >= 2) {
+            P2 = s_p[(tb + A - 2) & (NT - 1)];
+            P1 = s_p[(tb + A - 1) & (NT - 1)];
+        } else {   // A == 1 (lane 0 never changes, so A >= 1)
+            P2 = P1;
+            P1 = s_p[tb];
+        }
+        if (r == A) { s_misc[2] = nT; s_misc[3] = nW; }
+        if (r == NT - 1) { s_misc[4] = nT + dT; s_misc[5] = nW + dW; }
+        if (t < 4) s_min[(par ^ 1) * 4 + t] = NT;
+        __syncthreads();   // S5
+        const long long endT = s_misc[4], endW = s_misc[5];
+        if (A < NT) { Tb = s_misc[2]; Wb = s_misc[3]; }
+        else { Tb = endT; Wb = endW; }
+        if (r >= A) { T = nT; Wv = nW; }
+        else { T = endT + (long long)r * endW; Wv = endW; }
+        tb = (tb + A) & (NT - 1);
+        par ^= 1;
+        // refill the ring behind the new base
+        {
+            const long long bii = Tb >> 32;
+            const long long target = ((bii < lo_min ? lo_min : bii) & ~31LL) + R;
+            for (long long i = x_fill + t; i < target; i += NT)
+                if (i >= lo_min && i < n) cp_async8(&s_x[i & RM], in + i);
+            if (target > x_fill) x_fill = target;
+        }
+    }
+    overflow = __syncthreads_or(overflow);
+    if (t == 0) {
+        MmSegOut so;
+        so.n_sym = count;
+        so.overflow = overflow;
+        so.iters = iters;
+        so.windows = iters;
+        segout[j] = so;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// 32-bit variant of the chain kernel (the one normally used): identical algorithm, but the state
+// is held as (int sample index, 2^-32 fraction, 2^-32 offset of omega from omega_mid) and the
+// per-lane increments are scanned as 32-bit deviations from the base lane's omega; only the
+// cross-warp prefix is 64-bit.  Valid when every per-symbol deviation is far below half a sample
+// and n < 2^30 (checked on the host, which otherwise launches mm_chain_kernel).
+// ---------------------------------------------------------------------------------------
+__host__ __device__ inline size_t mm_chain32_smem_bytes(int NT, int R)
+{
+    return sizeof(float) * MM_TAB_PAD + sizeof(float2) * 2 * NT + sizeof(long long) * NT + sizeof(int) * (NT + 32 + 32 + 8) +
+           sizeof(unsigned) * 8 + sizeof(float2) * (size_t)R;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int n, int L, int W, int nseg, int cap_seg,
+                  MmState *__restrict__ entry, MmState *__restrict__ exit_, const MmState *__restrict__ carried,
+                  const unsigned char *__restrict__ redo, MmSegOut *__restrict__ segout, const float *__restrict__ table,
+                  MmParams prm, int mode, long long in_ch_stride, long long stage_ch_stride, int R)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float *s_tab = reinterpret_cast<float *>(s_raw);
+    float2 *s_p = reinterpret_cast<float2 *>(s_tab + MM_TAB_PAD);   // [2][NT] interpolants, double buffered
+    long long *s_nT = reinterpret_cast<long long *>(s_p + 2 * NT);  // [NT] new (ii, fraction) of every lane
+    int *s_nW = reinterpret_cast<int *>(s_nT + NT);                 // [NT] new omega offset
+    int *s_wD = s_nW + NT;                                          // [32] warp totals of dev
+    int *s_wW = s_wD + 32;                                          // [32] warp totals of dw
+    int *s_m32 = s_wW + 32;                                         // 0,1: base lane's in-warp exclusive (dev, dw)
+    unsigned *s_min = reinterpret_cast<unsigned *>(s_m32 + 8);      // [2][4]
+    float2 *s_x = reinterpret_cast<float2 *>(s_min + 8);            // [R] sample ring
+    constexpr int NW = NT / 32;
+    constexpr int BIG = 1 << 30;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int j = blockIdx.x, ch = blockIdx.y;
+    in += (size_t)ch * in_ch_stride;
+    stage += (size_t)ch * stage_ch_stride + (size_t)j * cap_seg;
+    entry += (size_t)ch * nseg;
+    exit_ += (size_t)ch * nseg;
+    segout += (size_t)ch * nseg;
+    if (mode == 1 && !redo[(size_t)ch * nseg + j]) return;
+    for (int i = t; i < 129 * 8; i += NT) {
+        const int k = i >> 3, tp = i & 7;
+        s_tab[tp * 129 + k] = table[i];
+    }
+    if (t < 8) s_min[t] = NT;
+
+    const int seg0 = (j == 0) ? -BIG : j * L;
+    const int seg1 = (j == nseg - 1) ? BIG : (j + 1) * L;
+    const int last_ok = n - MM_NTAPS;
+    MmState st;
+    bool have_entry;
+    if (mode == 0) {
+        const long long begin = (long long)j * L - W;
+        if (j == 0 || begin <= 0) {
+            st = carried[ch];
+        } else {
+            st.ii = begin;
+            st.mu = 0.5f;
+            st.omega = prm.omega_mid;
+            st.p0 = make_float2(0.f, 0.f);
+            st.p1 = make_float2(0.f, 0.f);
+        }
+        have_entry = false;
+    } else {
+        st = entry[j];
+        have_entry = true;
+    }
+    const float omid = prm.omega_mid;
+    const long long OM = (long long)(omid * MM_FIX);   // exact: omega_mid has 24 significant bits
+    // base lane (uniform): sample index, fraction, omega offset
+    int ii_b = (int)st.ii;
+    unsigned fr_b = (unsigned)(st.mu * MM_FIX);
+    int wr_b = (int)((st.omega - omid) * MM_FIX);
+    float2 P1 = st.p0, P2 = st.p1;
+    int tb = 0, count = 0, overflow = 0, iters = 0, par = 0;
+    // believed state of this lane
+    int ii, wr = wr_b;
+    unsigned fr;
+    {
+        const long long T = ((long long)ii_b << 32) + fr_b + (long long)t * (OM + wr_b);
+        ii = (int)(T >> 32);
+        fr = (unsigned)T;
+    }
+    int c_ii = -BIG, c_k = -1;
+    float2 p0 = make_float2(0.f, 0.f);
+    const int RM = R - 1;
+    const int lo_min = -MM_TAIL;
+    // ring: sample i sits in s_x[i & RM].  [x_ready - R, x_ready) is resident and visible to every thread;
+    // [x_ready, x_fill) is in flight (cp.async group of the previous iteration).
+    int x_fill = (ii_b < lo_min ? lo_min : ii_b) & ~31;
+    {
+        const int target = x_fill + R;
+        for (int i = x_fill + t; i < target; i += NT)
+            if (i >= lo_min && i < n) cp_async8(&s_x[i & RM], in + i);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        x_fill = target;
+    }
+    cp_async_wait_all();
+    int x_ready = x_fill;
+    __syncthreads();
+
+    for (;;) {
+        iters++;
+        float2 *sp = s_p + par * NT;
+        // ---- 1. interpolate at the believed state (skipped when (ii, k) did not move)
+        const float mu = (float)fr * MM_UNFIX;
+        const float om = fmaf((float)wr, MM_UNFIX, omid);   // exact
+        const int k = (int)rintf(mu * (float)MM_NSTEPS);
+        const bool inrange = (ii >= x_fill - R) && (ii >= lo_min) && (ii + MM_NTAPS <= x_ready) && (ii <= last_ok);
+        if (!inrange) {
+            p0 = make_float2(0.f, 0.f);
+            c_k = -1;
+        } else if (ii != c_ii || k != c_k) {
+            c_ii = ii;
+            c_k = k;
+            const int b = ii & RM;
+            float ar[4], ai[4];
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                const float t0 = s_tab[(7 - l) * 129 + k];
+                const float t1 = s_tab[(3 - l) * 129 + k];
+                const float2 a = s_x[(b + l) & RM], bb = s_x[(b + l + 4) & RM];
+                ar[l] = fmaf(t1, bb.x, t0 * a.x);
+                ai[l] = fmaf(t1, bb.y, t0 * a.y);
+            }
+            p0 = make_float2((ar[0] + ar[1]) + (ar[2] + ar[3]), (ai[0] + ai[1]) + (ai[2] + ai[3]));
+        }
+        sp[t] = p0;
+        __syncthreads();   // S1
+        // ---- 2. literal loop update
+        const int r = (t - tb) & (NT - 1);
+        float2 p1 = sp[(t - 1) & (NT - 1)], p2 = sp[(t - 2) & (NT - 1)];
+        if (r == 0) { p1 = P1; p2 = P2; }
+        if (r == 1) { p2 = P1; }
+        float mu2 = mu, om2 = om;
+        long long ii2l = 0;
+        mm_update(prm, p0, p1, p2, mu2, om2, ii2l);          // ii2l = floor(mu + omega' + gain_mu * mm): unused here
+        const long long Wb = OM + wr_b;
+        const unsigned fr2 = (unsigned)(mu2 * MM_FIX);
+        // deviation of this symbol's advance from the base omega in 2^-32 samples: the advance is
+        // ii2l * 2^32 + fr2 - fr, the base omega is Wb, and their difference is far below 2^31 in
+        // magnitude, so its low 32 bits are the whole value
+        const int dev = (int)(fr2 - fr - (unsigned)Wb);
+        const int dw = (int)((om2 - omid) * MM_FIX) - wr;
+        // ---- 3. inclusive scans in thread order
+        int iD = dev, iWd = dw;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, iD, o);
+            const int b = __shfl_up_sync(0xffffffffu, iWd, o);
+            if (lane >= o) { iD += a; iWd += b; }
+        }
+        if (lane == 31) { s_wD[wid] = iD; s_wW[wid] = iWd; }
+        if (t == tb) { s_m32[0] = iD - dev; s_m32[1] = iWd - dw; }
+        __syncthreads();   // S2
+        // ---- 4. cross-warp prefixes by warp-wide reductions of the warp totals (no serial second level):
+        // lane l holds warp l's totals; a 32-bit total is summed as two 16-bit halves so the 64-bit sum is exact
+        const int wtD = (lane < NW) ? s_wD[lane] : 0;
+        const int wtW = (lane < NW) ? s_wW[lane] : 0;
+        const int wb = tb >> 5;
+        const int selD = (lane < wid) ? wtD : 0, selB = (lane < wb) ? wtD : 0;
+        const long long preD = ((long long)__reduce_add_sync(0xffffffffu, selD >> 16) << 16) +
+                               (long long)__reduce_add_sync(0xffffffffu, (unsigned)(selD & 0xffff));
+        const long long preB = ((long long)__reduce_add_sync(0xffffffffu, selB >> 16) << 16) +
+                               (long long)__reduce_add_sync(0xffffffffu, (unsigned)(selB & 0xffff));
+        const long long totD = ((long long)__reduce_add_sync(0xffffffffu, wtD >> 16) << 16) +
+                               (long long)__reduce_add_sync(0xffffffffu, (unsigned)(wtD & 0xffff));
+        const int preW = __reduce_add_sync(0xffffffffu, (lane < wid) ? wtW : 0);
+        const int preWB = __reduce_add_sync(0xffffffffu, (lane < wb) ? wtW : 0);
+        const int totW = __reduce_add_sync(0xffffffffu, wtW);
+        const long long eD = preD + (long long)(iD - dev);
+        const int eW = preW + (iWd - dw);
+        const long long bD = preB + (long long)s_m32[0];
+        const int bW = preWB + s_m32[1];
+        const long long rotD = (t >= tb) ? eD - bD : totD - bD + eD;
+        const int rotW = (t >= tb) ? eW - bW : totW - bW + eW;
+        const long long Tb = ((long long)ii_b << 32) + fr_b;
+        const long long nT = Tb + (long long)r * Wb + rotD;
+        const int nii = (int)(nT >> 32);
+        const unsigned nfr = (unsigned)nT;
+        const int nwr = wr_b + rotW;
+        s_nT[t] = nT;
+        s_nW[t] = nwr;
+        const bool changed = (nii != ii) || (nfr != fr) || (nwr != wr) || !inrange;
+        const bool stopc = (nii > last_ok) || (nii >= seg1);
+        const unsigned m0 = __reduce_min_sync(0xffffffffu, changed ? (unsigned)r : (unsigned)NT);
+        const unsigned m1 = __reduce_min_sync(0xffffffffu, stopc ? (unsigned)r : (unsigned)NT);
+        if (lane == 0) {
+            if (m0 < NT) atomicMin(&s_min[par * 4 + 0], m0);
+            if (m1 < NT) atomicMin(&s_min[par * 4 + 1], m1);
+        }
+        if (!have_entry) {
+            const bool entc = (nii >= seg0);
+            const unsigned m2 = __reduce_min_sync(0xffffffffu, entc ? (unsigned)r : (unsigned)NT);
+            if (lane == 0 && m2 < NT) atomicMin(&s_min[par * 4 + 2], m2);
+        }
+        // the ring refill issued in the previous iteration must have landed before anyone reads it
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();   // S4
+        x_ready = x_fill;
+        const int A = (int)s_min[par * 4 + 0];
+        const int r_stop = (int)s_min[par * 4 + 1];
+        int r_ent = (int)s_min[par * 4 + 2];
+        const bool stop = (r_stop < NT) && (r_stop <= A);
+        const int hi = stop ? r_stop : A;
+        int lo = 0;
+        if (!have_entry) {
+            if (r_ent > r_stop) r_ent = r_stop;
+            if (r_ent <= hi && r_ent < NT) {
+                lo = r_ent;
+                if (r == r_ent) {
+                    float2 q1 = sp[(t - 1) & (NT - 1)], q2 = sp[(t - 2) & (NT - 1)];
+                    if (r == 0) { q1 = P1; q2 = P2; }
+                    if (r == 1) { q2 = P1; }
+                    MmState s;
+                    s.ii = nii;
+                    s.mu = (float)nfr * MM_UNFIX;
+                    s.omega = fmaf((float)nwr, MM_UNFIX, omid);
+                    s.p0 = q1;
+                    s.p1 = q2;
+                    entry[j] = s;
+                }
+                have_entry = true;
+            } else {
+                lo = hi;
+            }
+        }
+        if (r >= lo && r < hi) {
+            const int pos = count + (r - lo);
+            if (pos < cap_seg) stage[pos] = p0;
+            else overflow = 1;
+        }
+        count += (hi > lo) ? (hi - lo) : 0;
+        if (stop) {
+            if (r == r_stop) {
+                float2 q1 = sp[(t - 1) & (NT - 1)], q2 = sp[(t - 2) & (NT - 1)];
+                if (r == 0) { q1 = P1; q2 = P2; }
+                if (r == 1) { q2 = P1; }
+                MmState s;
+                s.ii = nii;
+                s.mu = (float)nfr * MM_UNFIX;
+                s.omega = fmaf((float)nwr, MM_UNFIX, omid);
+                s.p0 = q1;
+                s.p1 = q2;
+                exit_[j] = s;
+            }
+            break;
+        }
+        // ---- 5. slide: every thread derives the new base and the end state itself (no further barrier)
+        if (A >= 2) {
+            P2 = sp[(tb + A - 2) & (NT - 1)];
+            P1 = sp[(tb + A - 1) & (NT - 1)];
+        } else {
+            P2 = P1;
+            P1 = sp[tb];
+        }
+        // state after the last lane = base + NT base advances + all deviations
+        const long long endT = Tb + (long long)NT * Wb + totD;
+        const int endW = wr_b + totW;
+        long long Tn;
+        if (A < NT) {
+            const int ta = (tb + A) & (NT - 1);
+            Tn = s_nT[ta];
+            wr_b = s_nW[ta];
+        } else {
+            Tn = endT;
+            wr_b = endW;
+        }
+        ii_b = (int)(Tn >> 32);
+        fr_b = (unsigned)Tn;
+        if (r >= A) {
+            ii = nii; fr = nfr; wr = nwr;
+        } else {
+            const long long T = endT + (long long)r * (OM + endW);
+            ii = (int)(T >> 32);
+            fr = (unsigned)T;
+            wr = endW;
+        }
+        if (t < 4) s_min[(par ^ 1) * 4 + t] = NT;
+        tb = (tb + A) & (NT - 1);
+        par ^= 1;
+        {
+            const int target = ((ii_b < lo_min ? lo_min : ii_b) & ~31) + R;
+            for (int i = x_fill + t; i < target; i += NT)
+                if (i >= lo_min && i < n) cp_async8(&s_x[i & RM], in + i);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            if (target > x_fill) x_fill = target;
+        }
+    }
+    overflow = __syncthreads_or(overflow);
+    if (t == 0) {
+        MmSegOut so;
+        so.n_sym = count;
+        so.overflow = overflow;
+        so.iters = iters;
+        so.windows = iters;
         segout[j] = so;
     }
 }
