@@ -130,7 +130,7 @@ typedef struct {
     int64_t mm_seg, mm_warm;
     int32_t mm_lanes;            /* symbols per fixed-point window of the M&M chain kernel: 128/256/512/1024
                                     (+0x10000: force the generic 64-bit kernel; tests) */
-    int32_t reserved;
+    int32_t loop_kernel;         /* AGC/Costas kernel: 0 default, 1 one thread per segment, 2 window-Newton warp chains */
 } xrd_tuning;
 int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t);
 
@@ -140,6 +140,7 @@ typedef struct {
     uint64_t agc_rounds, costas_rounds, mm_rounds;       /* fix-up rounds run */
     uint64_t agc_redo, costas_redo, mm_redo;             /* segments re-run */
     uint64_t mm_windows, mm_iters;                       /* fixed-point windows / iterations */
+    uint64_t agc_iters, costas_iters;                    /* window-Newton iterations (all warps) */
     float ms_fir_dec, ms_agc, ms_fir_rrc, ms_costas, ms_mm;  /* device time of the last call (CUDA events) */
 } xrd_stats;
 int xrd_get_stats(xrd_demod *d, xrd_stats *s);
@@ -172,6 +173,8 @@ int xrd_clock_recovery_create(int device, float omega, float gain_omega, float m
 int xrd_stage_work(xrd_stage *s, const float *in, float *out, int length);
 /* segmentation override for a stage (samples); 0 keeps defaults */
 int xrd_stage_set_tuning(xrd_stage *s, int64_t seg, int64_t warm);
+/* AGC / Costas kernel choice as xrd_tuning.loop_kernel (tests; results never depend on it) */
+int xrd_stage_set_loop_kernel(xrd_stage *s, int kernel);
 void xrd_stage_destroy(xrd_stage *s);
 const char *xrd_stage_last_error(const xrd_stage *s);
 

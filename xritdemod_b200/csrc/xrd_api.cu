@@ -3,6 +3,7 @@
 // include/xrd.h.  Compiled with -fmad=false (see xrd_kernels.cuh).
 #include "../../include/xrd.h"
 #include "xrd_kernels.cuh"
+#include "xrd_wn.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -262,13 +263,21 @@ template <class S> __global__ void take_last_kernel(S *carried, const S *exit_, 
 constexpr int SEG_NTH = 64;   // segments (threads) per CTA of the segment loop kernel
 constexpr int SEG_TS = 16;    // samples per register tile (one 128-byte line)
 
+constexpr int WN_K = 4;       // samples per lane of a window-Newton chain (window = 128 samples per warp)
+constexpr int WN_CKPT = 2048; // samples between state checkpoints (power of two >= 32 * WN_K)
+
 template <class LOOP> struct SegStage {
     typedef typename LOOP::State State;
     typename LOOP::Params prm;
+    // thread-per-segment kernel (seg_loop_kernel): short segments, one thread each
     int L = 4096, W = 32768;
+    // window-Newton kernel (wn_loop_kernel): one warp per segment, long segments.  Lw == 0: as many
+    // segments as the device holds chains (chains_per_sm warps per SM), at least Lw_min samples each
+    int Lw = 0, Ww = 32768, Lw_min = 16384, chains_per_sm = 8;
+    bool use_wn = true;
     bool use_mirror = false;
-    int nch = 1;
-    DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list;
+    int nch = 1, sm_count = 148;
+    DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list, d_ckpt, d_iters;
     int *h_nredo = nullptr;   // pinned
     uint64_t rounds = 0, redone = 0, escalations = 0;
     State s_init;
@@ -285,7 +294,12 @@ template <class LOOP> struct SegStage {
         d_carried.ensure(sizeof(State) * nch);
         reset();
         d_nredo.ensure(sizeof(int));
+        d_iters.ensure(sizeof(unsigned long long));
+        XRD_CUDA(cudaMemset(d_iters.p, 0, sizeof(unsigned long long)));
         if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, sizeof(int)));
+        int dev = 0;
+        XRD_CUDA(cudaGetDevice(&dev));
+        XRD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     ~SegStage()
     {
@@ -297,31 +311,58 @@ template <class LOOP> struct SegStage {
         XRD_CUDA(cudaMemcpy(&s, d_carried.as<State>() + ch, sizeof(State), cudaMemcpyDeviceToHost));
         return s;
     }
-
-    void launch(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n, int Ls, int Ws, int nseg,
-                int n_work, int mode, long long in_stride, long long out_stride)
+    uint64_t wn_iters()
     {
-        const int grid = (n_work + SEG_NTH - 1) / SEG_NTH;
-        XRD_LAUNCH(c, (seg_loop_kernel<LOOP, SEG_TS>), grid, SEG_NTH, 0, st, in, out, n, Ls, Ws, nseg, n_work,
-                   d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(), prm, mode, in_stride,
-                   out_stride);
+        unsigned long long v = 0;
+        if (d_iters.p) cudaMemcpy(&v, d_iters.p, sizeof v, cudaMemcpyDeviceToHost);
+        return v;
+    }
+
+    void launch(Counters &c, cudaStream_t st, bool wn, const float2 *in, float2 *out, long long n, int Ls, int Ws, int nseg,
+                int n_work, int ncp, int mode, long long in_stride, long long out_stride)
+    {
+        if (wn) {
+            const int grid = (n_work + WN_WARPS - 1) / WN_WARPS;
+            XRD_LAUNCH(c, (wn_loop_kernel<LOOP, WN_K>), grid, WN_WARPS * 32, wn_smem_bytes<WN_K>(), st, in, out, n, Ls, Ws, nseg,
+                       n_work, d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(),
+                       d_ckpt.as<State>(), ncp, WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride);
+        } else {
+            const int grid = (n_work + SEG_NTH - 1) / SEG_NTH;
+            XRD_LAUNCH(c, (seg_loop_kernel<LOOP, SEG_TS>), grid, SEG_NTH, 0, st, in, out, n, Ls, Ws, nseg, n_work,
+                       d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(), prm, mode, in_stride,
+                       out_stride);
+        }
     }
 
     void run(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n, long long in_stride,
              long long out_stride)
     {
         if (n <= 0) return;
-        int Ls = std::max(L, SEG_TS);
-        int Ws = ((std::max(W, 0) + SEG_TS - 1) / SEG_TS) * SEG_TS;
+        const bool wn = use_wn;
+        int Ls, Ws;
+        if (wn) {
+            long long l = Lw;
+            if (l <= 0) {
+                const int per_ch = std::max(1, sm_count * chains_per_sm / nch);
+                l = std::max<long long>(Lw_min, (n + per_ch - 1) / per_ch);
+            }
+            Ls = (int)std::min<long long>(std::max<long long>(l, 32), 1 << 30);
+            Ws = std::max(Ww, 0);
+        } else {
+            Ls = std::max(L, SEG_TS);
+            Ws = ((std::max(W, 0) + SEG_TS - 1) / SEG_TS) * SEG_TS;
+        }
         for (int attempt = 0;; attempt++) {
             const int nseg = (int)((n + Ls - 1) / Ls);
             const size_t tot = (size_t)nseg * nch;
+            const int ncp = Ls / WN_CKPT + 2;
             d_entry.ensure(sizeof(State) * tot);
             d_exit.ensure(sizeof(State) * tot);
             d_redo.ensure(tot);
             d_list.ensure(sizeof(int) * tot);
             if (use_mirror) d_mirror.ensure(tot);
-            launch(c, st, in, out, n, Ls, Ws, nseg, (int)tot, 0, in_stride, out_stride);
+            if (wn) d_ckpt.ensure(sizeof(State) * tot * ncp);
+            launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 0, in_stride, out_stride);
             bool escalate = false;
             for (int round = 0; nseg > 1 && round < nseg; round++) {
                 XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, sizeof(int), st));
@@ -333,14 +374,15 @@ template <class LOOP> struct SegStage {
                 const int nr = *h_nredo;
                 if (nr == 0) break;
                 // speculation that mostly fails (weak signal: slow AGC; no lock) would need a fix-up round per
-                // segment: redo the pass with longer warm-ups and segments instead (bounded)
-                if (round == 0 && (size_t)nr * 100 > tot * 95 && tot >= 64 && attempt < 3) {
+                // segment: redo the pass with longer warm-ups and segments instead (bounded).  Re-runs of the
+                // window kernel stop as soon as they merge with the trajectory in place, so it never needs this.
+                if (!wn && round == 0 && (size_t)nr * 100 > tot * 95 && tot >= 64 && attempt < 3) {
                     escalate = true;
                     break;
                 }
                 rounds++;
                 redone += (uint64_t)nr;
-                launch(c, st, in, out, n, Ls, Ws, nseg, nr, 1, in_stride, out_stride);
+                launch(c, st, wn, in, out, n, Ls, Ws, nseg, nr, ncp, 1, in_stride, out_stride);
             }
             if (!escalate) {
                 XRD_LAUNCH(c, (take_last_kernel<State>), (nch + 127) / 128, 128, 0, st, d_carried.as<State>(),
@@ -353,6 +395,14 @@ template <class LOOP> struct SegStage {
         }
     }
 };
+
+// the window kernel holds the AGC gain in 2^-40 fixed point: needs a finite clamp well inside 2^23
+static bool agc_wn_ok(float max_gain) { return max_gain > 0.f && max_gain < 4.0e6f; }
+// the window kernel's Costas step removes at most one turn per sample (CostasLoopK::step_sel)
+static bool costas_wn_ok(const CostasParams &p)
+{
+    return std::fabs(p.alpha) + std::max(std::fabs(p.max_freq), std::fabs(p.min_freq)) < 6.0f;
+}
 
 // ---------------------------------------------------------------------------------------
 // M&M stage
@@ -864,12 +914,15 @@ int xrd_create(const xrd_config *cfg, xrd_demod **out)
         d->agc.prm = AgcParams{cfg->agc_rate, cfg->agc_ref, cfg->agc_max_gain};               // :447
         d->agc.L = 2048;
         d->agc.W = 16384;
+        d->agc.Ww = 16384;
+        d->agc.use_wn = agc_wn_ok(cfg->agc_max_gain);
         AgcState a0{cfg->agc_gain, 0.f};
         d->agc.init(d->nch, a0);
         float ca, cb;
         costas_gains(cfg->pll_alpha, ca, cb);                                                 // :448
         d->costas.prm = CostasParams{ca, cb, 1.0f, -1.0f};
         d->costas.use_mirror = true;
+        d->costas.use_wn = costas_wn_ok(d->costas.prm);
         d->costas.L = 4096;
         d->costas.W = 32768;
         CostasState c0{0.f, 0.f};
@@ -1060,10 +1113,15 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
     if (!d || !t) return XRD_E_ARG;
     if (t->agc_seg < 0 || t->agc_warm < 0 || t->costas_seg < 0 || t->costas_warm < 0 || t->mm_seg < 0 || t->mm_warm < 0)
         return XRD_E_ARG;
-    if (t->agc_seg) d->agc.L = t->agc_seg;
-    if (t->agc_warm) d->agc.W = t->agc_warm;
-    if (t->costas_seg) d->costas.L = t->costas_seg;
-    if (t->costas_warm) d->costas.W = t->costas_warm;
+    if (t->agc_seg) d->agc.L = d->agc.Lw = t->agc_seg;
+    if (t->agc_warm) d->agc.W = d->agc.Ww = t->agc_warm;
+    if (t->costas_seg) d->costas.L = d->costas.Lw = t->costas_seg;
+    if (t->costas_warm) d->costas.W = d->costas.Ww = t->costas_warm;
+    if (t->loop_kernel == 1) d->agc.use_wn = d->costas.use_wn = false;
+    else if (t->loop_kernel == 2) {
+        d->agc.use_wn = agc_wn_ok(d->agc.prm.max_gain);
+        d->costas.use_wn = costas_wn_ok(d->costas.prm);
+    }
     if (t->mm_seg) d->mm.L = std::max<long long>(t->mm_seg, 64);
     if (t->mm_lanes) d->mm.nt = t->mm_lanes & 0xffff;
     d->mm.force64 = (t->mm_lanes & 0x10000) != 0;
@@ -1084,6 +1142,8 @@ int xrd_get_stats(xrd_demod *d, xrd_stats *s)
     s->mm_redo = d->mm.redone;
     s->mm_windows = d->mm.windows;
     s->mm_iters = d->mm.iters;
+    s->agc_iters = d->agc.wn_iters();
+    s->costas_iters = d->costas.wn_iters();
     s->ms_fir_dec = d->ms[0];
     s->ms_agc = d->ms[1];
     s->ms_fir_rrc = d->ms[2];
@@ -1196,6 +1256,8 @@ int xrd_agc_create(int device, float rate, float reference, float gain, float ma
         s->agc.prm = AgcParams{rate, reference, max_gain};
         s->agc.L = 2048;
         s->agc.W = 16384;
+        s->agc.Ww = 16384;
+        s->agc.use_wn = agc_wn_ok(max_gain);
         s->agc.init(1, AgcState{gain, 0.f});
         return (int)XRD_OK;
     });
@@ -1219,6 +1281,7 @@ int xrd_costas_create(int device, float loop_bw, int order, xrd_stage **out)
         costas_gains(loop_bw, a, b);
         s->costas.prm = CostasParams{a, b, 1.0f, -1.0f};
         s->costas.use_mirror = true;
+        s->costas.use_wn = costas_wn_ok(s->costas.prm);
         s->costas.L = 4096;
         s->costas.W = 32768;
         s->costas.init(1, CostasState{0.f, 0.f});
@@ -1296,12 +1359,12 @@ int xrd_stage_set_tuning(xrd_stage *s, int64_t seg, int64_t warm)
     if (!s || seg < 0 || warm < 0) return XRD_E_ARG;
     switch (s->kind) {
     case xrd_stage::AGC:
-        if (seg) s->agc.L = (int)seg;
-        if (warm) s->agc.W = (int)warm;
+        if (seg) s->agc.L = s->agc.Lw = (int)seg;
+        if (warm) s->agc.W = s->agc.Ww = (int)warm;
         break;
     case xrd_stage::COSTAS:
-        if (seg) s->costas.L = (int)seg;
-        if (warm) s->costas.W = (int)warm;
+        if (seg) s->costas.L = s->costas.Lw = (int)seg;
+        if (warm) s->costas.W = s->costas.Ww = (int)warm;
         break;
     case xrd_stage::MM:
         if (seg) s->mm.L = std::max<long long>(seg, 64);
@@ -1310,6 +1373,15 @@ int xrd_stage_set_tuning(xrd_stage *s, int64_t seg, int64_t warm)
     default:
         break;
     }
+    return XRD_OK;
+}
+
+int xrd_stage_set_loop_kernel(xrd_stage *s, int kernel)
+{
+    if (!s || kernel < 0 || kernel > 2) return XRD_E_ARG;
+    const bool wn = kernel != 1;
+    if (s->kind == xrd_stage::AGC) s->agc.use_wn = wn && agc_wn_ok(s->agc.prm.max_gain);
+    if (s->kind == xrd_stage::COSTAS) s->costas.use_wn = wn && costas_wn_ok(s->costas.prm);
     return XRD_OK;
 }
 

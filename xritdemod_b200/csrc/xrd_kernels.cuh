@@ -203,6 +203,7 @@ struct AgcLoop {
         s.gain = g;
         return y;
     }
+    __device__ static __forceinline__ float2 step_sel(State &s, const Params &p, float2 x) { return step(s, p, x); }
     __device__ static __forceinline__ bool same(const State &a, const State &b) { return a.gain == b.gain; }
     // speculative start: the gain that puts the mean level of the first samples on the reference
     __device__ static __forceinline__ State guess(const Params &p, const float2 *x, int m)
@@ -244,6 +245,28 @@ struct CostasLoopK {
             phase = (float)((double)phase + 6.283185307179586);
         if (freq > p.max_freq) freq = p.max_freq;
         else if (freq < p.min_freq) freq = p.min_freq;
+        s.phase = phase;
+        s.freq = freq;
+        return y;
+    }
+    // The same step without branches, for the window kernel.  |freq| <= 1 after the clamp and
+    // alpha < 0.83 for every loop bandwidth, so one conditional turn is exactly what the while loops
+    // above do for any state inside +-2*pi (the host checks alpha + max|freq| < 2*pi before using it).
+    __device__ static __forceinline__ float2 step_sel(State &s, const Params &p, float2 x)
+    {
+        float sn, cs;
+        nco_sincos(-s.phase, sn, cs);
+        float2 y;
+        y.x = x.x * cs - x.y * sn;
+        y.y = x.x * sn + x.y * cs;
+        const float err = clip_bl(y.x * y.y, 1.0f);
+        float freq = s.freq + p.beta * err;
+        float phase = s.phase + freq + p.alpha * err;
+        const float T = 6.28318500518798828125f;
+        const double turn = (phase > T) ? -6.283185307179586 : 6.283185307179586;
+        const float wrapped = (float)((double)phase + turn);
+        phase = (phase > T || phase < -T) ? wrapped : phase;
+        freq = (freq > p.max_freq) ? p.max_freq : ((freq < p.min_freq) ? p.min_freq : freq);
         s.phase = phase;
         s.freq = freq;
         return y;

@@ -1,0 +1,362 @@
+// xrd_wn.cuh -- "window Newton" runner for the sample-rate feedback loops (AGC, Costas).
+//
+// A feedback loop is a literal scalar recurrence s[i+1] = F(s[i], x[i]) in FP32 (LOOP::step, the
+// same function the one-thread-per-segment kernel uses).  One warp advances ONE such chain, but
+// NT = 32*K samples at a time:
+//
+//   * every slot of a ring of NT consecutive samples holds a BELIEVED state for its sample;
+//   * each iteration all slots apply the literal step to their believed state: o = F(s, x);
+//   * the state differences o - s are taken exactly (fixed point, int64) and prefix-summed in
+//     sample order from the exact state of the base sample; the sums are the next believed states
+//     (if every believed state up to a slot was true, the sum telescopes to the true state of the
+//     next slot exactly -- the truth is a fixed point of this map, and because F contracts and FP32
+//     rounding snaps nearby states together, the iteration converges to it from a linear
+//     extrapolation in a handful of rounds, ~25 samples per round at NT = 128);
+//   * acceptance is literal: slot r is exact iff slot r-1 is exact and believed[r] == o[r-1]
+//     bit for bit.  The leading exact run of A >= 1 samples is emitted, the base moves to sample A
+//     with the literal state o[A-1], and the freed slots re-enter at the far end of the window.
+//
+// Proposals may be arbitrarily wrong (overflow, wrong 2*pi branch, unrepresentable tiny values):
+// that only costs iterations, never correctness, because nothing is accepted without the
+// literal check.  The result is the sequential trajectory, exactly.
+#pragma once
+#include "xrd_kernels.cuh"
+
+namespace xrd {
+
+// ---- exact wide views of the loop states: doubles (differences of two FP32 states and their
+// running sums are exact in FP64 for every value the loops normally take; B200 runs DADD at half
+// the FP32 rate, and an inexact sum only costs an iteration) ----
+struct AgcWn {
+    static constexpr int NS = 1;
+    __device__ static __forceinline__ void widen(const AgcState &s, double *f) { f[0] = (double)s.gain; }
+    __device__ static __forceinline__ AgcState narrow(const double *f)
+    {
+        AgcState s;
+        s.gain = (float)f[0];
+        s.pad = 0.f;
+        return s;
+    }
+    __device__ static __forceinline__ bool in_range(const AgcState &) { return true; }
+    __device__ static __forceinline__ void normalise(double *) {}
+    __device__ static __forceinline__ void extrapolate(const double *e, int, double *o) { o[0] = e[0]; }
+};
+
+struct CostasWn {
+    static constexpr int NS = 2;
+    __device__ static __forceinline__ void widen(const CostasState &s, double *f)
+    {
+        f[0] = (double)s.phase;
+        f[1] = (double)s.freq;
+    }
+    __device__ static __forceinline__ CostasState narrow(const double *f)
+    {
+        CostasState s;
+        s.phase = (float)f[0];
+        s.freq = (float)f[1];
+        return s;
+    }
+    // a believed phase outside the literal loop's range (a sum across a turn that is not settled yet, an
+    // extrapolation past +-2*pi) is brought back by whole turns, as the loop itself would have
+    __device__ static __forceinline__ bool in_range(const CostasState &s) { return fabsf(s.phase) <= 6.2831855f; }
+    __device__ static __forceinline__ void normalise(double *f)
+    {
+        const double T = 6.283185307179586;
+        double p = f[0];
+        p -= T * rint(p * (0.5 / T) * 0.999999);   // whole turns towards zero-ish; |p| <= 2*pi afterwards for sane p
+        p = (p > T) ? p - T : p;
+        p = (p < -T) ? p + T : p;
+        f[0] = (p > T || p < -T || p != p) ? 0.0 : p;
+        f[1] = fmin(fmax(f[1], -1.0), 1.0);
+    }
+    __device__ static __forceinline__ void extrapolate(const double *e, int r, double *o)
+    {
+        o[0] = fma((double)r, e[1], e[0]);
+        o[1] = e[1];
+    }
+};
+
+template <class LOOP> struct WnOf;
+template <> struct WnOf<AgcLoop> { typedef AgcWn type; };
+template <> struct WnOf<CostasLoopK> { typedef CostasWn type; };
+
+constexpr int WN_WARPS = 4;   // independent chains per CTA
+
+template <int K> __host__ __device__ constexpr int wn_ring() { return 32 * K * 4; }   // samples per warp ring (power of two)
+template <int K> __host__ __device__ constexpr size_t wn_smem_bytes() { return sizeof(float2) * wn_ring<K>() * WN_WARPS; }
+
+// checkpoint use of a run
+enum { WN_CK_NONE = 0, WN_CK_RECORD = 1, WN_CK_COMPARE = 2 };
+
+template <class State> __device__ __forceinline__ State wn_shfl(const State &v, int src)
+{
+    // State is a pair of 32-bit words in both loops
+    float2 t = *reinterpret_cast<const float2 *>(&v);
+    t.x = __shfl_sync(0xffffffffu, t.x, src);
+    t.y = __shfl_sync(0xffffffffu, t.y, src);
+    return *reinterpret_cast<State *>(&t);
+}
+
+// Runs samples [s_begin, s_end) of x (segment-relative indices, s_begin a multiple of K;
+// x[s_begin..s_end) addressable) from the exact state `st`, returns the exact state after sample
+// s_end-1.  WRITE: outputs go to y (s_begin >= 0).  CK: exact states before samples that are
+// multiples of C (a power of two >= 32*K; 0 < i < s_end) are recorded in / compared with ck[i / C];
+// in compare mode the run stops at the first checkpoint that equals the stored one (the
+// trajectories have merged: everything after it is already in place) and *merged is set.
+// Warp-collective.
+//
+// Slot lane*K + k of the ring holds one sample; the base (oldest unfinished sample) always sits in
+// slot 0 of a lane (the window slides by multiples of K; up to K-1 accepted samples stay in the
+// window one more round), so a slot's rank is ((lane - tbl) & 31) * K + k.
+template <class LOOP, int K, bool WRITE, int CK>
+__device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, int s_end,
+                                                       typename LOOP::State st, const typename LOOP::Params &prm, float2 *ring,
+                                                       typename LOOP::State *ck, int C, bool *merged, unsigned long long *iters_out)
+{
+    typedef typename LOOP::State State;
+    typedef typename WnOf<LOOP>::type WN;
+    constexpr int NS = WN::NS;
+    constexpr int NT = 32 * K;
+    constexpr int RS = wn_ring<K>();
+    constexpr int MARGIN = 2 * NT;
+    const int lane = threadIdx.x & 31;
+
+    int base = s_begin, tbl = 0;
+    State bs[K];          // believed state before the sample of slot lane*K + k
+    float2 xs[K];         // that sample
+    double basew[NS];
+    WN::widen(st, basew);
+    State base_state = st;
+
+    // ring: sample i lives in ring[i & (RS-1)]; [fill - RS, fill) resident or in flight
+    int fill = s_begin;
+    {
+        const int target = min(s_begin + NT + MARGIN, s_end);
+        for (int i = fill + lane; i < target; i += 32) cp_async8(&ring[i & (RS - 1)], x + i);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        fill = max(fill, target);
+        cp_async_wait_all();
+        __syncwarp();
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int r = lane * K + k;
+        double f[NS];
+        WN::extrapolate(basew, r, f);
+        WN::normalise(f);
+        bs[k] = (r == 0) ? st : WN::narrow(f);
+        const int i = base + r;
+        xs[k] = (i < s_end) ? ring[i & (RS - 1)] : make_float2(0.f, 0.f);
+    }
+    unsigned long long iters = 0;
+    bool done_merged = false;
+
+    while (base < s_end) {
+        iters++;
+        // ---- 1. literal step of every slot, exact state differences summed within the lane
+        State o[K];
+        float2 yo[K];
+        double li[K][NS];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            o[k] = bs[k];
+            yo[k] = LOOP::step_sel(o[k], prm, xs[k]);
+            double fo[NS], fs[NS];
+            WN::widen(o[k], fo);
+            WN::widen(bs[k], fs);
+#pragma unroll
+            for (int c = 0; c < NS; c++) li[k][c] = k ? li[k - 1][c] + (fo[c] - fs[c]) : (fo[c] - fs[c]);
+        }
+        // ---- 2. warp scan of the lane totals (slot order); state before this lane's slot 0 if all before it is true
+        double total[NS], lanebase[NS];
+#pragma unroll
+        for (int c = 0; c < NS; c++) {
+            double v = li[K - 1][c];
+#pragma unroll
+            for (int ofs = 1; ofs < 32; ofs <<= 1) {
+                const double a = __shfl_up_sync(0xffffffffu, v, ofs);
+                if (lane >= ofs) v += a;
+            }
+            const double we = v - li[K - 1][c];
+            total[c] = __shfl_sync(0xffffffffu, v, 31);
+            const double b = __shfl_sync(0xffffffffu, we, tbl);
+            lanebase[c] = basew[c] + ((lane < tbl) ? (we - b) + total[c] : (we - b));
+        }
+        // ---- 3. acceptance: believed[r] == o[r-1], literally, for a leading run of ranks
+        State prev[K];
+        prev[0] = wn_shfl(o[K - 1], (lane + 31) & 31);
+#pragma unroll
+        for (int k = 1; k < K; k++) prev[k] = o[k - 1];
+        const int lr = ((lane - tbl) & 31) * K;   // rank of this lane's slot 0
+        unsigned mybad = NT;
+#pragma unroll
+        for (int k = K - 1; k >= 0; k--)
+            if (!LOOP::same(bs[k], prev[k])) mybad = lr + k;
+        if (lr == 0 && LOOP::same(bs[0], prev[0]) == false) {
+            // rank 0 is the exact base whatever precedes it in the ring: look past it
+            mybad = NT;
+#pragma unroll
+            for (int k = K - 1; k >= 1; k--)
+                if (!LOOP::same(bs[k], prev[k])) mybad = k;
+        }
+        const int A = min((int)__reduce_min_sync(0xffffffffu, mybad), s_end - base);   // >= 1 exact samples
+        if (base + A >= s_end) {
+            // ---- the run ends inside the window: flush, pick the state after the last sample
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (WRITE && lr + k < A) y[base + lr + k] = yo[k];
+            const int ra = A - 1;
+            State sel = o[0];
+#pragma unroll
+            for (int k = 1; k < K; k++)
+                if (k == (ra % K)) sel = o[k];
+            base_state = wn_shfl(sel, (tbl + ra / K) & 31);
+            base += A;
+            break;
+        }
+        const int Ap = A & ~(K - 1);   // slide by whole lanes
+        const bool freed = lr < Ap;
+        if (Ap) {
+            // ---- 4. emit the samples that leave the window; exact state after them = o of rank Ap-1
+            if (WRITE && freed) {
+#pragma unroll
+                for (int k = 0; k < K; k++) y[base + lr + k] = yo[k];
+            }
+            const State nb = wn_shfl(o[K - 1], (tbl + Ap / K - 1) & 31);
+            // checkpoint: the multiple of C in (base, base+Ap], if any (at most one: C >= NT)
+            if (CK != WN_CK_NONE) {
+                const int i0 = (base + Ap) & ~(C - 1);
+                if (i0 > base && i0 > 0 && i0 < s_end) {
+                    const int r0 = i0 - base;   // K .. Ap, a multiple of K
+                    const State cs = wn_shfl(prev[0], (tbl + r0 / K) & 31);   // state before rank r0 (== nb when r0 == Ap)
+                    bool mrg = false;
+                    if (lane == 0) {
+                        State *slot = ck + (i0 >> (31 - __clz(C)));
+                        if (CK == WN_CK_COMPARE && LOOP::same(*slot, cs)) mrg = true;
+                        else *slot = cs;
+                    }
+                    if (__any_sync(0xffffffffu, mrg)) {
+                        done_merged = true;
+                        break;
+                    }
+                }
+            }
+            base_state = nb;
+            // the group issued two iterations ago covers every sample the freed slots need now
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+            __syncwarp();
+        }
+        // ---- 5. next believed states: freed slots are extrapolated from the state after the window, accepted
+        // slots that stay keep their (verified) state, the first unaccepted slot takes the literal o[A-1], the
+        // rest take the prefix sums
+        double endw[NS];
+#pragma unroll
+        for (int c = 0; c < NS; c++) endw[c] = basew[c] + total[c];
+        bool odd = false;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int r = lr + k;
+            double f[NS], fe[NS];
+            WN::extrapolate(endw, r, fe);
+#pragma unroll
+            for (int c = 0; c < NS; c++) {
+                const double fk = k ? lanebase[c] + li[k - 1][c] : lanebase[c];
+                f[c] = freed ? fe[c] : fk;
+            }
+            const State prop = WN::narrow(f);
+            const State nbs = (freed || r > A) ? prop : ((r == A) ? prev[k] : bs[k]);
+            odd |= !WN::in_range(nbs);
+            bs[k] = nbs;
+            if (freed) {
+                const int i = base + NT + r;
+                xs[k] = (i < s_end) ? ring[i & (RS - 1)] : make_float2(0.f, 0.f);
+            }
+        }
+        if (odd) {
+            // rare: some believed phase of this lane left the loop's range; redo them with whole turns removed
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int r = lr + k;
+                if ((freed || r > A) && !WN::in_range(bs[k])) {
+                    double f[NS];
+                    if (freed) WN::extrapolate(endw, r, f);
+                    else {
+#pragma unroll
+                        for (int c = 0; c < NS; c++) f[c] = k ? lanebase[c] + li[k - 1][c] : lanebase[c];
+                    }
+                    WN::normalise(f);
+                    bs[k] = WN::narrow(f);
+                }
+            }
+        }
+        if (Ap) {
+            WN::widen(base_state, basew);
+            tbl = (tbl + Ap / K) & 31;
+            base += Ap;
+            const int target = min(base + NT + MARGIN, s_end);
+            for (int i = fill + lane; i < target; i += 32) cp_async8(&ring[i & (RS - 1)], x + i);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            fill = max(fill, target);
+        }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    if (merged) *merged = done_merged;
+    if (iters_out) *iters_out += iters;
+    return base_state;
+}
+
+// Segment-parallel loop kernel on window-Newton chains: one warp per work item, same contract as
+// seg_loop_kernel (mode 0: speculative warm-up + segment; mode 1: re-run from entry[g]), plus
+// checkpoints of the exact state every C samples so that a re-run stops as soon as it has merged
+// with the trajectory already in place.
+template <class LOOP, int K>
+__global__ void __launch_bounds__(WN_WARPS * 32)
+wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, int L, int W, int nseg, int n_work,
+               typename LOOP::State *__restrict__ entry, typename LOOP::State *__restrict__ exit_,
+               const typename LOOP::State *__restrict__ carried, const int *__restrict__ list,
+               typename LOOP::State *__restrict__ ckpt, int ncp, int C, unsigned long long *__restrict__ iters_total,
+               typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride)
+{
+    extern __shared__ __align__(16) unsigned char wn_smem[];
+    typedef typename LOOP::State State;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2 *ring = reinterpret_cast<float2 *>(wn_smem) + (size_t)wid * wn_ring<K>();
+    const int w = blockIdx.x * WN_WARPS + wid;
+    if (w >= n_work) return;
+    const int g = (mode == 0) ? w : list[w];
+    const int ch = g / nseg, j = g - ch * nseg;
+    const long long seg0 = (long long)j * L;
+    const int len = (int)min((long long)L, n - seg0);
+    const float2 *x = in + (size_t)ch * in_ch_stride + seg0;
+    float2 *y = out + (size_t)ch * out_ch_stride + seg0;
+    State *ck = ckpt + (size_t)g * ncp;
+    unsigned long long iters = 0;
+    State st;
+    if (mode == 0) {
+        const bool from_carried = (j == 0 || seg0 - W <= 0);
+        int s_begin;
+        if (from_carried) {
+            st = carried[ch];
+            s_begin = (int)-seg0;
+        } else {
+            s_begin = -W;
+            float2 first[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) first[i] = __ldg(x + s_begin + i);
+            st = LOOP::guess(prm, first, 16);
+        }
+        if (s_begin < 0) st = wn_run<LOOP, K, false, WN_CK_NONE>(x, y, s_begin, 0, st, prm, ring, nullptr, C, nullptr, &iters);
+        if (lane == 0) entry[g] = st;
+        st = wn_run<LOOP, K, true, WN_CK_RECORD>(x, y, 0, len, st, prm, ring, ck, C, nullptr, &iters);
+        if (lane == 0) exit_[g] = st;
+    } else {
+        st = entry[g];
+        bool merged = false;
+        st = wn_run<LOOP, K, true, WN_CK_COMPARE>(x, y, 0, len, st, prm, ring, ck, C, &merged, &iters);
+        if (lane == 0 && !merged) exit_[g] = st;
+    }
+    if (lane == 0 && iters_total) atomicAdd(iters_total, iters);
+}
+
+}  // namespace xrd

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "xrd_demod_batch", "xrd_demod_device", "xrd_soft_i8", "xrd_get_state", "xrd_reset", "xrd_stream", "xrd_set_tuning", "xrd_get_stats",
     "xrd_design_rrc", "xrd_design_lowpass", "xrd_mmse_table", "xrd_costas_gains",
     "xrd_fir_create", "xrd_agc_create", "xrd_costas_create", "xrd_clock_recovery_create", "xrd_stage_work",
-    "xrd_stage_set_tuning", "xrd_stage_destroy", "xrd_stage_last_error", "xrd_device_check", "xrd_version",
+    "xrd_stage_set_tuning", "xrd_stage_set_loop_kernel", "xrd_stage_destroy", "xrd_stage_last_error", "xrd_device_check", "xrd_version",
 ]
 
 
@@ -61,7 +61,7 @@ class LoopState(C.Structure):
 class Tuning(C.Structure):
     _fields_ = [
         ("agc_seg", C.c_int32), ("agc_warm", C.c_int32), ("costas_seg", C.c_int32), ("costas_warm", C.c_int32),
-        ("mm_seg", C.c_int64), ("mm_warm", C.c_int64), ("mm_lanes", C.c_int32), ("reserved", C.c_int32),
+        ("mm_seg", C.c_int64), ("mm_warm", C.c_int64), ("mm_lanes", C.c_int32), ("loop_kernel", C.c_int32),
     ]
 
 
@@ -69,7 +69,8 @@ class Stats(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_uint64), ("agc_rounds", C.c_uint64), ("costas_rounds", C.c_uint64),
         ("mm_rounds", C.c_uint64), ("agc_redo", C.c_uint64), ("costas_redo", C.c_uint64), ("mm_redo", C.c_uint64),
-        ("mm_windows", C.c_uint64), ("mm_iters", C.c_uint64), ("ms_fir_dec", C.c_float), ("ms_agc", C.c_float),
+        ("mm_windows", C.c_uint64), ("mm_iters", C.c_uint64), ("agc_iters", C.c_uint64),
+        ("costas_iters", C.c_uint64), ("ms_fir_dec", C.c_float), ("ms_agc", C.c_float),
         ("ms_fir_rrc", C.c_float), ("ms_costas", C.c_float), ("ms_mm", C.c_float),
     ]
 
@@ -128,6 +129,7 @@ def lib():
                                             C.POINTER(vp)]
     L.xrd_stage_work.argtypes = [vp, vp, vp, C.c_int]
     L.xrd_stage_set_tuning.argtypes = [vp, C.c_int64, C.c_int64]
+    L.xrd_stage_set_loop_kernel.argtypes = [vp, C.c_int]
     L.xrd_stage_destroy.argtypes = [vp]
     L.xrd_stage_destroy.restype = None
     L.xrd_stage_last_error.argtypes = [vp]
@@ -209,6 +211,9 @@ class _Stage:
 
     def set_tuning(self, seg=0, warm=0):
         self._check(lib().xrd_stage_set_tuning(self._h, seg, warm))
+
+    def set_loop_kernel(self, kernel):
+        self._check(lib().xrd_stage_set_loop_kernel(self._h, kernel))
 
     def close(self):
         if self._h:
