@@ -42,8 +42,8 @@ def _stale(target, sources):
 
 
 def build_libxrd(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, "xrd_api.cu"), os.path.join(CSRC, "xrd_kernels.cuh"),
-            os.path.join(ROOT, "include", "xrd.h")]
+    srcs = [os.path.join(CSRC, "xrd_api.cu")] + sorted(
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "xrd.h")]
     if force or _stale(LIBXRD, srcs):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIBXRD, srcs[0]]
         subprocess.check_call(cmd)

@@ -277,7 +277,7 @@ template <class LOOP> struct SegStage {
     bool use_wn = true;
     bool use_mirror = false;
     int nch = 1, sm_count = 148;
-    DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list, d_ckpt, d_iters;
+    DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list, d_ckpt, d_iters, d_psi, d_adv;
     int *h_nredo = nullptr;   // pinned
     uint64_t rounds = 0, redone = 0, escalations = 0;
     State s_init;
@@ -318,6 +318,13 @@ template <class LOOP> struct SegStage {
         return v;
     }
 
+    void resolve(Counters &c, cudaStream_t st, int nseg, int Ls, int Ws) { resolve_impl(c, st, nseg, Ls, Ws, d_entry.as<State>()); }
+    void resolve_impl(Counters &c, cudaStream_t st, int nseg, int Ls, int Ws, CostasState *e)
+    {
+        XRD_LAUNCH(c, costas_resolve_kernel, nch, 32, 0, st, nseg, Ls, Ws, e, d_adv.as<float>(), (int *)nullptr);
+    }
+    void resolve_impl(Counters &, cudaStream_t, int, int, int, AgcState *) {}
+
     void launch(Counters &c, cudaStream_t st, bool wn, const float2 *in, float2 *out, long long n, int Ls, int Ws, int nseg,
                 int n_work, int ncp, int mode, long long in_stride, long long out_stride)
     {
@@ -346,8 +353,9 @@ template <class LOOP> struct SegStage {
                 const int per_ch = std::max(1, sm_count * chains_per_sm / nch);
                 l = std::max<long long>(Lw_min, (n + per_ch - 1) / per_ch);
             }
-            Ls = (int)std::min<long long>(std::max<long long>(l, 32), 1 << 30);
-            Ws = std::max(Ww, 0);
+            l = std::min<long long>(std::max<long long>(l, 32), 1 << 30);
+            Ls = (int)((l + WN_CKPT - 1) / WN_CKPT * WN_CKPT);   // checkpoints and carrier-phase blocks tile the segment
+            Ws = (std::max(Ww, 0) + 31) / 32 * 32;
         } else {
             Ls = std::max(L, SEG_TS);
             Ws = ((std::max(W, 0) + SEG_TS - 1) / SEG_TS) * SEG_TS;
@@ -362,7 +370,22 @@ template <class LOOP> struct SegStage {
             d_list.ensure(sizeof(int) * tot);
             if (use_mirror) d_mirror.ensure(tot);
             if (wn) d_ckpt.ensure(sizeof(State) * tot * ncp);
-            launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 0, in_stride, out_stride);
+            if (wn && use_mirror && nseg > 1 && n >= 2 * CPB) {
+                // Costas: warm-ups, then put the entry states on one carrier-phase branch, then the segments
+                launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 2, in_stride, out_stride);
+                const long long nblk = n / CPB;
+                d_psi.ensure(sizeof(float) * (size_t)nblk * nch);
+                d_adv.ensure(sizeof(float) * tot);
+                dim3 g1((unsigned)((nblk + 255) / 256), nch);   // 8 warps x 32 blocks per CTA
+                XRD_LAUNCH(c, costas_block_phase_kernel, g1, 256, 0, st, in, d_psi.as<float>(), nblk, in_stride, nblk);
+                dim3 g2(nseg, nch);
+                XRD_LAUNCH(c, costas_seg_advance_kernel, g2, 256, 0, st, d_psi.as<float>(), d_adv.as<float>(), nseg, Ls / CPB,
+                           nblk, nblk);
+                resolve(c, st, nseg, Ls, Ws);
+                launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 3, in_stride, out_stride);
+            } else {
+                launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 0, in_stride, out_stride);
+            }
             bool escalate = false;
             for (int round = 0; nseg > 1 && round < nseg; round++) {
                 XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, sizeof(int), st));
@@ -425,13 +448,14 @@ static int next_pow2(long long v)
 
 struct MmStage {
     MmParams prm;
-    long long L = 0, W = 1600000;   // L == 0: one segment per SM (set per call); W: speculative warm-up (samples)
+    long long L = 0, W = 800000;    // L == 0: one segment per SM (set per call); W: speculative warm-up (samples)
     long long Lmin = 262144;
     int nt = 0;                     // lanes per chain (0 = auto)
     bool force64 = false;           // tests: always use the generic 64-bit chain kernel
     int sm_count = 148;
     int nch = 1;
-    DevBuf d_table, d_carried, d_entry, d_exit, d_redo, d_nredo, d_segout, d_offsets, d_stage, d_overflow;
+    DevBuf d_table, d_carried, d_entry, d_exit, d_redo, d_nredo, d_segout, d_offsets, d_stage, d_overflow, d_ckpt;
+    int ck_spacing = 65536;         // samples between chain checkpoints
     int *h_nredo = nullptr;
     std::vector<long long> h_offsets;
     uint64_t rounds = 0, redone = 0, windows = 0, iters = 0;
@@ -483,13 +507,15 @@ struct MmStage {
                           32.0 * dev_max < 0.45 && 2.0 * prm.omega_lim + prm.gain_mu < 0.45 && prm.omega_mid < 1024.f;
         if (fast) {
             const size_t smem32 = mm_chain32_smem_bytes(NT, R);
+            const int ncp = (int)(Lseg / ck_spacing) + 2;
+            d_ckpt.ensure(sizeof(MmCk) * (size_t)grid.x * grid.y * ncp);
 #define XRD_MM_CHAIN32(NTV)                                                                                              \
     do {                                                                                                                 \
         XRD_CUDA(cudaFuncSetAttribute(mm_chain32_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32)); \
         XRD_LAUNCH(c, mm_chain32_kernel<NTV>, grid, NTV, smem32, st, in, d_stage.as<float2>(), (int)n, (int)Lseg, (int)W, \
                    nseg, (int)cap_seg, d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(),             \
                    d_redo.as<unsigned char>(), d_segout.as<MmSegOut>(), d_table.as<float>(), prm, mode, in_stride,       \
-                   stage_stride, R);                                                                                     \
+                   stage_stride, R, d_ckpt.as<MmCk>(), ncp, ck_spacing);                                                 \
     } while (0)
             if (NT >= 1024) XRD_MM_CHAIN32(1024);
             else if (NT == 512) XRD_MM_CHAIN32(512);

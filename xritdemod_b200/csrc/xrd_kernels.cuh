@@ -532,6 +532,15 @@ struct MmSegOut {
     int windows;
 };
 
+// checkpoint of a chain: the exact state before the first symbol at or after a sample boundary, and how many
+// symbols the segment had emitted by then.  A re-run that reaches a checkpoint with both unchanged has merged
+// with the trajectory already in place and stops there.
+struct MmCk {
+    MmState st;
+    int count;
+    int pad;
+};
+
 // mode 0: first pass (warm-up from a speculative state, or from `carried` when the warm-up reaches
 // the chunk start); mode 1: re-run of segments flagged in `redo` from entry[j].
 __global__ void __launch_bounds__(32)
@@ -990,7 +999,8 @@ __global__ void __launch_bounds__(NT)
 mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int n, int L, int W, int nseg, int cap_seg,
                   MmState *__restrict__ entry, MmState *__restrict__ exit_, const MmState *__restrict__ carried,
                   const unsigned char *__restrict__ redo, MmSegOut *__restrict__ segout, const float *__restrict__ table,
-                  MmParams prm, int mode, long long in_ch_stride, long long stage_ch_stride, int R)
+                  MmParams prm, int mode, long long in_ch_stride, long long stage_ch_stride, int R, MmCk *__restrict__ ckpt,
+                  int ncp, int C)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     float *s_tab = reinterpret_cast<float *>(s_raw);
@@ -1017,6 +1027,11 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
         s_tab[tp * 129 + k] = table[i];
     }
     if (t < 8) s_min[t] = NT;
+    __shared__ int s_merged;
+    if (t == 0) s_merged = 0;
+    MmCk *ck = ckpt ? ckpt + ((size_t)ch * nseg + j) * ncp : nullptr;
+    int next_ck = j * L + C, ck_idx = 0;   // sample boundary of the next checkpoint
+    bool merged = false;
 
     const int seg0 = (j == 0) ? -BIG : j * L;
     const int seg1 = (j == nseg - 1) ? BIG : (j + 1) * L;
@@ -1168,6 +1183,10 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
             const unsigned m2 = __reduce_min_sync(0xffffffffu, entc ? (unsigned)r : (unsigned)NT);
             if (lane == 0 && m2 < NT) atomicMin(&s_min[par * 4 + 2], m2);
         }
+        if (ck) {
+            const unsigned m3 = __reduce_min_sync(0xffffffffu, (nii >= next_ck) ? (unsigned)r : (unsigned)NT);
+            if (lane == 0 && m3 < NT) atomicMin(&s_min[par * 4 + 3], m3);
+        }
         // the ring refill issued in the previous iteration must have landed before anyone reads it
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();   // S4
@@ -1204,7 +1223,35 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
             if (pos < cap_seg) stage[pos] = p0;
             else overflow = 1;
         }
+        if (ck && have_entry) {
+            // checkpoint: first symbol at or after sample next_ck, if its state is exact already (r_ck <= hi)
+            const int r_ck = (int)s_min[par * 4 + 3];
+            if (r_ck < NT && r_ck <= hi && r_ck >= lo && next_ck < seg1 && ck_idx < ncp) {
+                if (r == r_ck) {
+                    float2 q1 = sp[(t - 1) & (NT - 1)], q2 = sp[(t - 2) & (NT - 1)];
+                    if (r == 0) { q1 = P1; q2 = P2; }
+                    if (r == 1) { q2 = P1; }
+                    MmCk c;
+                    c.st.ii = nii;
+                    c.st.mu = (float)nfr * MM_UNFIX;
+                    c.st.omega = fmaf((float)nwr, MM_UNFIX, omid);
+                    c.st.p0 = q1;
+                    c.st.p1 = q2;
+                    c.count = count + (r_ck - lo);
+                    c.pad = 0;
+                    if (mode == 1 && mm_same(ck[ck_idx].st, c.st) && ck[ck_idx].count == c.count) s_merged = 1;
+                    else ck[ck_idx] = c;
+                }
+                if (mode == 1) {
+                    __syncthreads();
+                    merged = (s_merged != 0);
+                }
+                next_ck += C;
+                ck_idx++;
+            }
+        }
         count += (hi > lo) ? (hi - lo) : 0;
+        if (merged) break;
         if (stop) {
             if (r == r_stop) {
                 float2 q1 = sp[(t - 1) & (NT - 1)], q2 = sp[(t - 2) & (NT - 1)];
@@ -1264,10 +1311,18 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
     overflow = __syncthreads_or(overflow);
     if (t == 0) {
         MmSegOut so;
-        so.n_sym = count;
-        so.overflow = overflow;
-        so.iters = iters;
-        so.windows = iters;
+        if (merged) {
+            // the rest of the segment is in place from the earlier pass: keep its totals
+            so = segout[j];
+            so.overflow |= overflow;
+            so.iters += iters;
+            so.windows += iters;
+        } else {
+            so.n_sym = count;
+            so.overflow = overflow;
+            so.iters = iters;
+            so.windows = iters;
+        }
         segout[j] = so;
     }
 }

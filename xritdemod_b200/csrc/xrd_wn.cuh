@@ -307,9 +307,11 @@ __device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict_
 }
 
 // Segment-parallel loop kernel on window-Newton chains: one warp per work item, same contract as
-// seg_loop_kernel (mode 0: speculative warm-up + segment; mode 1: re-run from entry[g]), plus
-// checkpoints of the exact state every C samples so that a re-run stops as soon as it has merged
-// with the trajectory already in place.
+// seg_loop_kernel (mode 0: speculative warm-up + segment; mode 1: re-run of the listed segments from
+// entry[g]), plus checkpoints of the exact state every C samples so that a re-run stops as soon as
+// it has merged with the trajectory already in place, and the first pass in two halves -- mode 2:
+// warm-ups only (entry states), mode 3: every segment from entry[g] -- so that the host can put
+// the Costas entries on one carrier-phase branch in between (costas_resolve_kernel).
 template <class LOOP, int K>
 __global__ void __launch_bounds__(WN_WARPS * 32)
 wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, int L, int W, int nseg, int n_work,
@@ -324,7 +326,7 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
     float2 *ring = reinterpret_cast<float2 *>(wn_smem) + (size_t)wid * wn_ring<K>();
     const int w = blockIdx.x * WN_WARPS + wid;
     if (w >= n_work) return;
-    const int g = (mode == 0) ? w : list[w];
+    const int g = (mode == 1) ? list[w] : w;
     const int ch = g / nseg, j = g - ch * nseg;
     const long long seg0 = (long long)j * L;
     const int len = (int)min((long long)L, n - seg0);
@@ -333,7 +335,8 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
     State *ck = ckpt + (size_t)g * ncp;
     unsigned long long iters = 0;
     State st;
-    if (mode == 0) {
+    if (mode == 0 || mode == 2) {
+        // speculative warm-up: the state at the segment start (mode 2 stops there)
         const bool from_carried = (j == 0 || seg0 - W <= 0);
         int s_begin;
         if (from_carried) {
@@ -348,15 +351,122 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
         }
         if (s_begin < 0) st = wn_run<LOOP, K, false, WN_CK_NONE>(x, y, s_begin, 0, st, prm, ring, nullptr, C, nullptr, &iters);
         if (lane == 0) entry[g] = st;
+    }
+    if (mode == 3) st = entry[g];
+    if (mode == 0 || mode == 3) {
         st = wn_run<LOOP, K, true, WN_CK_RECORD>(x, y, 0, len, st, prm, ring, ck, C, nullptr, &iters);
         if (lane == 0) exit_[g] = st;
-    } else {
+    } else if (mode == 1) {
         st = entry[g];
         bool merged = false;
         st = wn_run<LOOP, K, true, WN_CK_COMPARE>(x, y, 0, len, st, prm, ring, ck, C, &merged, &iters);
         if (lane == 0 && !merged) exit_[g] = st;
     }
     if (lane == 0 && iters_total) atomicAdd(iters_total, iters);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Costas: which of the two stable lock points (carrier phase, carrier phase + pi) a cold warm-up
+// ends on is a coin flip, and a segment run on the wrong one has to be re-run in full.  The
+// carrier phase itself is observable without the loop: arg(sum x^2) over a short block is twice
+// the carrier phase, and the wrapped differences of consecutive blocks sum to its continuous
+// advance across a segment.  That predicts the branch a segment's entry state must be on given its
+// predecessor's, so the entries can be put on one branch before the segments are run.  A wrong
+// prediction (no lock, very low SNR) only costs the re-run it would have cost anyway.
+// ---------------------------------------------------------------------------------------
+constexpr int CPB = 32;   // samples per carrier-phase block
+
+// psi[b] = arg(sum of x^2 over block b); one warp per 32 blocks, coalesced 16-byte loads
+__global__ void __launch_bounds__(256)
+costas_block_phase_kernel(const float2 *__restrict__ in, float *__restrict__ psi, long long nblk, long long in_ch_stride,
+                          long long psi_ch_stride)
+{
+    const int lane = threadIdx.x & 31;
+    const long long wtile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // 32 blocks = 1024 samples
+    const int ch = blockIdx.y;
+    const long long b0 = wtile * 32;
+    if (b0 >= nblk) return;
+    const float2 *p2 = in + (size_t)ch * in_ch_stride + b0 * CPB;
+    const float4 *p = reinterpret_cast<const float4 *>(p2);
+    const bool vec = (reinterpret_cast<unsigned long long>(p2) & 15) == 0;
+    const int nb = (int)min(32LL, nblk - b0);
+    float mr = 0.f, mi = 0.f;
+#pragma unroll 4
+    for (int it = 0; it < 16; it++) {
+        // float4 number it*32 + lane of the tile holds samples 2*(it*32+lane), +1: block it*2 + lane/16
+        float sr = 0.f, si = 0.f;
+        if (it * 2 + (lane >> 4) < nb) {
+            float4 q;
+            if (vec) q = __ldg(p + it * 32 + lane);
+            else {
+                const float2 a = __ldg(p2 + 2 * (it * 32 + lane)), b = __ldg(p2 + 2 * (it * 32 + lane) + 1);
+                q = make_float4(a.x, a.y, b.x, b.y);
+            }
+            sr = (q.x * q.x - q.y * q.y) + (q.z * q.z - q.w * q.w);
+            si = 2.f * (q.x * q.y + q.z * q.w);
+        }
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+            sr += __shfl_xor_sync(0xffffffffu, sr, o);
+            si += __shfl_xor_sync(0xffffffffu, si, o);
+        }
+        // lanes 0-15 hold block 2*it, lanes 16-31 block 2*it+1; park them in lanes 2*it, 2*it+1
+        const float r1 = __shfl_sync(0xffffffffu, sr, 16), i1 = __shfl_sync(0xffffffffu, si, 16);
+        const float r0 = __shfl_sync(0xffffffffu, sr, 0), i0 = __shfl_sync(0xffffffffu, si, 0);
+        if (lane == 2 * it) { mr = r0; mi = i0; }
+        if (lane == 2 * it + 1) { mr = r1; mi = i1; }
+    }
+    if (lane < nb) psi[(size_t)ch * psi_ch_stride + b0 + lane] = atan2f(mi, mr);
+}
+
+// adv[g] = continuous carrier-phase advance from the start of segment g to the start of segment g+1
+__global__ void __launch_bounds__(256)
+costas_seg_advance_kernel(const float *__restrict__ psi, float *__restrict__ adv, int nseg, int blk_per_seg, long long nblk,
+                          long long psi_ch_stride)
+{
+    __shared__ double s_part[8];
+    const int j = blockIdx.x, ch = blockIdx.y;
+    const float *ps = psi + (size_t)ch * psi_ch_stride;
+    const long long b0 = (long long)j * blk_per_seg;
+    double acc = 0.0;
+    for (long long b = b0 + threadIdx.x; b < b0 + blk_per_seg && b + 1 < nblk; b += blockDim.x) {
+        float d = ps[b + 1] - ps[b];
+        d = (d > 3.14159265f) ? d - 6.28318531f : ((d < -3.14159265f) ? d + 6.28318531f : d);
+        acc += (double)d;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_part[w];
+        adv[(size_t)ch * nseg + j] = (float)(0.5 * t);
+    }
+}
+
+// puts the warm-up entry states of a channel on the branch of segment 0 (which starts from the exact state)
+__global__ void costas_resolve_kernel(int nseg, int L, int W, CostasState *__restrict__ entry, const float *__restrict__ adv,
+                                      int *__restrict__ n_flipped)
+{
+    const int ch = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    CostasState *e = entry + (size_t)ch * nseg;
+    const float *a = adv + (size_t)ch * nseg;
+    float prev = e[0].phase;
+    int flips = 0;
+    for (int j = 1; j < nseg; j++) {
+        float ph = e[j].phase;
+        const bool exact = ((long long)j * L - W <= 0);   // this segment ran from the carried state: already on the true branch
+        if (!exact && cosf(ph - (prev + a[j - 1])) < 0.f) {
+            ph = (ph > 0.f) ? ph - 3.14159265358979f : ph + 3.14159265358979f;
+            e[j].phase = ph;
+            flips++;
+        }
+        prev = ph;
+    }
+    if (n_flipped) atomicAdd(n_flipped, flips);
 }
 
 }  // namespace xrd
