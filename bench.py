@@ -277,17 +277,27 @@ def run_b200(args):
     ms_per_step = agg["elapsed_ms"] / args.steps
     value = agg["msps"]
 
-    # ---- roofline of the dominant stage kernel (device time measured live, CUDA events on the stage's stream)
+    # ---- roofline of the dominant kernel: device time of its stage measured live (CUDA events recorded on the
+    # demodulator's own stream around the stage, xrd_get_stats), algorithmic bytes of SURVEY.md 8(d)
     peak, peak_src = peaks()
     dom = max(stage_ms, key=lambda k: stage_ms[k])
     dom_ms = stage_ms[dom] / args.steps
-    kernel_of = {"ms_mm": "mm_seg_kernel", "ms_costas": "seg_loop_kernel<CostasLoopK>", "ms_agc": "seg_loop_kernel<AgcLoop>",
-                 "ms_fir_rrc": "fir1_kernel", "ms_fir_dec": "fird_kernel"}
+    kernel_of = {"ms_mm": "mm_chain32_kernel<1024>", "ms_costas": "wn_loop_kernel<CostasLoopK,4>",
+                 "ms_agc": "wn_loop_kernel<AgcLoop,4>", "ms_fir_rrc": "fir1_kernel", "ms_fir_dec": "fird_kernel"}
     alg_bytes = n * BYTES_PER_SAMPLE
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:   # DRAM bytes of that kernel from the committed ncu --set full capture (profiles/), per stage pass
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tr.get("samples") == n:
+            traffic = tr.get(kernel_of[dom])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": kernel_of[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
+                "note": "kernel_ms = all launches of that kernel in one step (first pass + certified re-runs); the "
+                        "feedback loops are latency/issue-bound exact recurrences, not HBM-bound (DESIGN.md)",
                 "chain_achieved": alg_bytes / (ms_per_step * 1e-3) / 1e9,
                 "chain_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                 "stage_ms": {k: v / args.steps for k, v in stage_ms.items()}}

@@ -99,19 +99,48 @@ def test_stage_state_carries_across_ragged_calls(gpu, xrd, stages):
         assert_bitexact(np.concatenate(parts), s[dst], "%s in ragged calls" % dst)
 
 
-def test_small_segments_force_fixups(gpu, xrd, stages):
-    """tiny segments / warm-ups make speculation fail often: the certified hand-off must repair it"""
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_small_segments_force_fixups(gpu, xrd, stages, kernel):
+    """tiny segments / warm-ups make speculation fail often: the certified hand-off must repair it.
+    kernel 1: one thread per segment; kernel 2: window-Newton warp chains (re-runs stop at merged checkpoints)"""
     s = stages["hrit"]
     a = xrd.AGC()
+    a.set_loop_kernel(kernel)
     a.set_tuning(512, 64)
     assert_bitexact(a.Work(s["x"][:200000]), s["agc"][:200000], "AGC tiny segments")
     c = xrd.CostasLoop()
+    c.set_loop_kernel(kernel)
     c.set_tuning(4096, 512)
     assert_bitexact(c.Work(s["rrc"][:200000]), s["costas"][:200000], "Costas tiny segments")
     gm = np.float32(0.0037)
     m = xrd.ClockRecovery(s["sps"], gm * gm / np.float32(4), 0.5, gm, 0.005)
     m.set_tuning(20000, 30000)
     check_symbols(m.Work(s["costas"]), s["sym"], "M&M small segments")
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("mode", ["hrit", "lrit"])
+def test_loop_kernels_agree(gpu, xrd, oracle, mode, kernel):
+    """the chain result does not depend on which AGC/Costas kernel ran"""
+    _, x = make_signal(mode, 1 << 21)
+    ref = oracle.Chain(oracle.config(mode == "hrit")).process(x)
+    d = xrd.Demodulator(mode=mode)
+    d.set_tuning(loop_kernel=kernel)
+    check_symbols(d.demod(x), ref, "chain with loop kernel %d" % kernel)
+    st = d.stats()
+    assert (st["costas_iters"] > 0) == (kernel == 2)
+
+
+@pytest.mark.parametrize("df_hz,channel", [(0.0, 3), (-900.0, 4), (350.0, 5)])
+def test_costas_branch_resolution_over_carrier_offsets(gpu, xrd, oracle, df_hz, channel):
+    """segments whose cold warm-up locks on carrier+pi are put on the true branch before they run (block phase of
+    x^2); zero, negative and positive carrier offsets, many short segments"""
+    _, x = make_signal("hrit", 1 << 20, channel=channel, carrier_hz=df_hz)
+    ch = oracle.Chain(oracle.config(True))
+    _, taps = ch.process(x, taps=True)
+    c = xrd.CostasLoop()
+    c.set_tuning(32768, 16384)
+    assert_bitexact(c.Work(taps["rrc"]), taps["costas"], "Costas, df %g Hz" % df_hz)
 
 
 # ------------------------------------------------------------------ the chain (processSamples)
