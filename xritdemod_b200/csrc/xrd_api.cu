@@ -940,7 +940,8 @@ int xrd_create(const xrd_config *cfg, xrd_demod **out)
         d->agc.prm = AgcParams{cfg->agc_rate, cfg->agc_ref, cfg->agc_max_gain};               // :447
         d->agc.L = 2048;
         d->agc.W = 16384;
-        d->agc.Ww = 16384;
+        d->agc.Ww = 8192;            // the AGC contracts fast: short warm-ups, twice the chains
+        d->agc.chains_per_sm = 16;
         d->agc.use_wn = agc_wn_ok(cfg->agc_max_gain);
         AgcState a0{cfg->agc_gain, 0.f};
         d->agc.init(d->nch, a0);
@@ -1282,7 +1283,8 @@ int xrd_agc_create(int device, float rate, float reference, float gain, float ma
         s->agc.prm = AgcParams{rate, reference, max_gain};
         s->agc.L = 2048;
         s->agc.W = 16384;
-        s->agc.Ww = 16384;
+        s->agc.Ww = 8192;
+        s->agc.chains_per_sm = 16;
         s->agc.use_wn = agc_wn_ok(max_gain);
         s->agc.init(1, AgcState{gain, 0.f});
         return (int)XRD_OK;

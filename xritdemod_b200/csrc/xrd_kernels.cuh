@@ -273,7 +273,7 @@ struct CostasLoopK {
     }
     __device__ static __forceinline__ bool same(const State &a, const State &b)
     {
-        return a.phase == b.phase && a.freq == b.freq;
+        return (a.phase == b.phase) & (a.freq == b.freq);
     }
     __device__ static __forceinline__ State guess(const Params &, const float2 *, int)
     {

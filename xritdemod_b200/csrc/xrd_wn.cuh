@@ -190,15 +190,10 @@ __device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict_
         const int lr = ((lane - tbl) & 31) * K;   // rank of this lane's slot 0
         unsigned mybad = NT;
 #pragma unroll
-        for (int k = K - 1; k >= 0; k--)
+        for (int k = K - 1; k >= 1; k--)
             if (!LOOP::same(bs[k], prev[k])) mybad = lr + k;
-        if (lr == 0 && LOOP::same(bs[0], prev[0]) == false) {
-            // rank 0 is the exact base whatever precedes it in the ring: look past it
-            mybad = NT;
-#pragma unroll
-            for (int k = K - 1; k >= 1; k--)
-                if (!LOOP::same(bs[k], prev[k])) mybad = k;
-        }
+        // rank 0 is the exact base whatever precedes it in the ring
+        if (lr != 0 && !LOOP::same(bs[0], prev[0])) mybad = lr;
         const int A = min((int)__reduce_min_sync(0xffffffffu, mybad), s_end - base);   // >= 1 exact samples
         if (base + A >= s_end) {
             // ---- the run ends inside the window: flush, pick the state after the last sample
@@ -249,46 +244,67 @@ __device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict_
         // ---- 5. next believed states: freed slots are extrapolated from the state after the window, accepted
         // slots that stay keep their (verified) state, the first unaccepted slot takes the literal o[A-1], the
         // rest take the prefix sums
-        double endw[NS];
+        // per lane: state before slot 0 (pb) and what the slots before slot k add to it (li[k-1])
+        double pb[NS];
 #pragma unroll
-        for (int c = 0; c < NS; c++) endw[c] = basew[c] + total[c];
+        for (int c = 0; c < NS; c++) pb[c] = lanebase[c];
+        if (freed) {
+            double endw[NS];
+#pragma unroll
+            for (int c = 0; c < NS; c++) endw[c] = basew[c] + total[c];
+            WN::extrapolate(endw, lr, pb);
+#pragma unroll
+            for (int k = 0; k < K - 1; k++) {
+                double z[NS], e[NS];
+#pragma unroll
+                for (int c = 0; c < NS; c++) z[c] = (c == NS - 1 && NS > 1) ? endw[c] : 0.0;   // frequency component drives the phase
+                if (NS > 1) {
+                    WN::extrapolate(z, k + 1, e);   // e[0] = (k+1) * endw[1], e[1] = endw[1]
+                    li[k][0] = e[0];
+                    li[k][NS - 1] = 0.0;
+                } else {
+                    li[k][0] = 0.0;
+                }
+            }
+            // the freed slots' samples: base + NT + lr .. +K-1 (contiguous in the ring: lr, base and RS are multiples of K)
+            const int i0 = base + NT + lr;
+#pragma unroll
+            for (int k = 0; k < K; k++) xs[k] = (i0 + k < s_end) ? ring[(i0 & (RS - 1)) + k] : make_float2(0.f, 0.f);
+        }
         bool odd = false;
+        State nbs[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            const int r = lr + k;
-            double f[NS], fe[NS];
-            WN::extrapolate(endw, r, fe);
+            double f[NS];
 #pragma unroll
-            for (int c = 0; c < NS; c++) {
-                const double fk = k ? lanebase[c] + li[k - 1][c] : lanebase[c];
-                f[c] = freed ? fe[c] : fk;
-            }
-            const State prop = WN::narrow(f);
-            const State nbs = (freed || r > A) ? prop : ((r == A) ? prev[k] : bs[k]);
-            odd |= !WN::in_range(nbs);
-            bs[k] = nbs;
-            if (freed) {
-                const int i = base + NT + r;
-                xs[k] = (i < s_end) ? ring[i & (RS - 1)] : make_float2(0.f, 0.f);
+            for (int c = 0; c < NS; c++) f[c] = k ? pb[c] + li[k - 1][c] : pb[c];
+            nbs[k] = WN::narrow(f);
+            odd |= !WN::in_range(nbs[k]);
+        }
+        if (!freed && lr <= A) {
+            // the one lane that holds the end of the accepted run: verified slots keep their state, the
+            // first unaccepted slot takes the literal o[A-1]
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (lr + k < A) nbs[k] = bs[k];
+                else if (lr + k == A) nbs[k] = prev[k];
             }
         }
         if (odd) {
-            // rare: some believed phase of this lane left the loop's range; redo them with whole turns removed
+            // rare: a believed phase of this lane left the loop's range; bring those back by whole turns
 #pragma unroll
             for (int k = 0; k < K; k++) {
-                const int r = lr + k;
-                if ((freed || r > A) && !WN::in_range(bs[k])) {
+                if (!WN::in_range(nbs[k])) {
                     double f[NS];
-                    if (freed) WN::extrapolate(endw, r, f);
-                    else {
 #pragma unroll
-                        for (int c = 0; c < NS; c++) f[c] = k ? lanebase[c] + li[k - 1][c] : lanebase[c];
-                    }
+                    for (int c = 0; c < NS; c++) f[c] = k ? pb[c] + li[k - 1][c] : pb[c];
                     WN::normalise(f);
-                    bs[k] = WN::narrow(f);
+                    nbs[k] = WN::narrow(f);
                 }
             }
         }
+#pragma unroll
+        for (int k = 0; k < K; k++) bs[k] = nbs[k];
         if (Ap) {
             WN::widen(base_state, basew);
             tbl = (tbl + Ap / K) & 31;
