@@ -273,7 +273,7 @@ template <class LOOP> struct SegStage {
     int L = 4096, W = 32768;
     // window-Newton kernel (wn_loop_kernel): one warp per segment, long segments.  Lw == 0: as many
     // segments as the device holds chains (chains_per_sm warps per SM), at least Lw_min samples each
-    int Lw = 0, Ww = 32768, Lw_min = 16384, chains_per_sm = 8;
+    int Lw = 0, Ww = 16384, Lw_min = 16384, chains_per_sm = 8;
     bool use_wn = true;
     bool use_mirror = false;
     int nch = 1, sm_count = 148;
@@ -321,7 +321,8 @@ template <class LOOP> struct SegStage {
     void resolve(Counters &c, cudaStream_t st, int nseg, int Ls, int Ws) { resolve_impl(c, st, nseg, Ls, Ws, d_entry.as<State>()); }
     void resolve_impl(Counters &c, cudaStream_t st, int nseg, int Ls, int Ws, CostasState *e)
     {
-        XRD_LAUNCH(c, costas_resolve_kernel, nch, 32, 0, st, nseg, Ls, Ws, e, d_adv.as<float>(), (int *)nullptr);
+        XRD_LAUNCH(c, costas_resolve_kernel, nch, 256, sizeof(unsigned) * ((nseg + 31) / 32), st, nseg, Ls, Ws, e,
+                   d_adv.as<float>(), (int *)nullptr);
     }
     void resolve_impl(Counters &, cudaStream_t, int, int, int, AgcState *) {}
 
@@ -595,7 +596,8 @@ struct MmStage {
         XRD_CUDA(cudaMemsetAsync(d_overflow.p, 0, sizeof(int), st));
         XRD_LAUNCH(c, mm_offsets_kernel, nch, 32, 0, st, nseg, d_segout.as<MmSegOut>(), d_offsets.as<long long>(),
                    d_overflow.as<int>());
-        dim3 cg(std::min(nseg, 1024), nch);
+        const int parts = std::max(1, std::min(64, (sm_count * 16) / std::max(1, nseg * nch)));
+        dim3 cg((unsigned)nseg * parts, nch);
         XRD_LAUNCH(c, mm_compact_kernel, cg, 256, 0, st, d_stage.as<float2>(), out, nseg, cap_seg,
                    d_segout.as<MmSegOut>(), d_offsets.as<long long>(), out_cap, stage_stride, out_stride);
         XRD_LAUNCH(c, mm_rebase_kernel, (nch + 127) / 128, 128, 0, st, d_carried.as<MmState>(), d_exit.as<MmState>(),

@@ -1359,13 +1359,15 @@ __global__ void mm_compact_kernel(const float2 *__restrict__ stage, float2 *__re
     out += (size_t)ch * out_ch_stride;
     segout += (size_t)ch * nseg;
     offsets += (size_t)ch * (nseg + 1);
-    for (int j = blockIdx.x; j < nseg; j += gridDim.x) {
-        const long long o = offsets[j];
-        const int c = segout[j].n_sym;
-        const float2 *src = stage + (size_t)j * cap_seg;
-        for (int i = threadIdx.x; i < c; i += blockDim.x)
-            if (o + i < out_cap) out[o + i] = src[i];
-    }
+    // blockIdx.x = segment * parts + part: every segment is copied by `parts` CTAs so that the grid fills the GPU
+    const int parts = gridDim.x / nseg;
+    const int j = blockIdx.x / parts, part = blockIdx.x - j * parts;
+    if (j >= nseg) return;
+    const long long o = offsets[j];
+    const int c = segout[j].n_sym;
+    const float2 *src = stage + (size_t)j * cap_seg;
+    for (long long i = (long long)part * blockDim.x + threadIdx.x; i < c; i += (long long)parts * blockDim.x)
+        if (o + i < out_cap) out[o + i] = src[i];
 }
 
 __global__ void mm_offsets_kernel(int nseg, const MmSegOut *__restrict__ segout, long long *__restrict__ offsets,

@@ -466,23 +466,41 @@ costas_seg_advance_kernel(const float *__restrict__ psi, float *__restrict__ adv
 __global__ void costas_resolve_kernel(int nseg, int L, int W, CostasState *__restrict__ entry, const float *__restrict__ adv,
                                       int *__restrict__ n_flipped)
 {
+    // flip[j] = entry j lies on the other branch than (entry j-1 advanced by adv[j-1]) -- independent of what
+    // happens to j-1, because flipping j-1 by pi flips the prediction by pi too: so the branch of j relative to
+    // segment 0 is the running parity of the flips, a prefix XOR done here by warp ballots
+    extern __shared__ unsigned s_par[];   // parity of each 32-segment word
     const int ch = blockIdx.x;
-    if (threadIdx.x != 0) return;
     CostasState *e = entry + (size_t)ch * nseg;
     const float *a = adv + (size_t)ch * nseg;
-    float prev = e[0].phase;
-    int flips = 0;
-    for (int j = 1; j < nseg; j++) {
-        float ph = e[j].phase;
-        const bool exact = ((long long)j * L - W <= 0);   // this segment ran from the carried state: already on the true branch
-        if (!exact && cosf(ph - (prev + a[j - 1])) < 0.f) {
-            ph = (ph > 0.f) ? ph - 3.14159265358979f : ph + 3.14159265358979f;
-            e[j].phase = ph;
-            flips++;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nwords = (nseg + 31) / 32;
+    for (int w = wid; w < nwords; w += nw) {
+        const int j = w * 32 + lane;
+        bool f = false;
+        if (j >= 1 && j < nseg) {
+            const bool exact = ((long long)j * L - W <= 0);          // ran from the carried state: on the true branch
+            f = !exact && (__cosf(e[j].phase - (e[j - 1].phase + a[j - 1])) < 0.f);
         }
-        prev = ph;
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_par[w] = m;
     }
-    if (n_flipped) atomicAdd(n_flipped, flips);
+    __syncthreads();
+    // exclusive parity prefix over the words (few: nseg / 32), serial in every thread's own loop below
+    for (int w = wid; w < nwords; w += nw) {
+        unsigned par = 0;
+        for (int q = 0; q < w; q++) par ^= __popc(s_par[q]) & 1u;
+        const int j = w * 32 + lane;
+        const unsigned m = s_par[w];
+        const unsigned upto = (lane == 31) ? m : (m & ((2u << lane) - 1u));
+        const bool flipped = ((par ^ (__popc(upto) & 1u)) & 1u) != 0;
+        const bool exact = (j < nseg) && ((long long)j * L - W <= 0);
+        if (j >= 1 && j < nseg && flipped && !exact) {
+            const float ph = e[j].phase;
+            e[j].phase = (ph > 0.f) ? ph - 3.14159265358979f : ph + 3.14159265358979f;
+        }
+    }
+    (void)n_flipped;
 }
 
 }  // namespace xrd
