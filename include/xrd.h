@@ -131,6 +131,8 @@ typedef struct {
     int32_t mm_lanes;            /* symbols per fixed-point window of the M&M chain kernel: 128/256/512/1024
                                     (+0x10000: force the generic 64-bit kernel; tests) */
     int32_t loop_kernel;         /* AGC/Costas kernel: 0 default, 1 one thread per segment, 2 window-Newton warp chains */
+    int32_t h2d_pieces;          /* host-input calls: copy/compute pieces (0 default = up to 2 of >= 16 M samples, 1 = one copy) */
+    int32_t reserved;
 } xrd_tuning;
 int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t);
 

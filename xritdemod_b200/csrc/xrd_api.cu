@@ -318,14 +318,15 @@ template <class LOOP> struct SegStage {
         return v;
     }
 
-    void resolve(Counters &c, cudaStream_t st, int nseg, int Ls, int Ws) { resolve_impl(c, st, nseg, Ls, Ws, d_entry.as<State>()); }
-    void resolve_impl(Counters &c, cudaStream_t st, int nseg, int Ls, int Ws, CostasState *e)
+    void resolve(Counters &c, cudaStream_t st, int nseg, int Ls, long long Ws) { resolve_impl(c, st, nseg, Ls, Ws, d_entry.as<State>()); }
+    void resolve_impl(Counters &c, cudaStream_t st, int nseg, int Ls, long long Ws, CostasState *e)
     {
         XRD_LAUNCH(c, costas_resolve_kernel, nch, 256, sizeof(unsigned) * ((nseg + 31) / 32), st, nseg, Ls, Ws, e,
                    d_adv.as<float>(), (int *)nullptr);
     }
-    void resolve_impl(Counters &, cudaStream_t, int, int, int, AgcState *) {}
+    void resolve_impl(Counters &, cudaStream_t, int, int, long long, AgcState *) {}
 
+    long long hist = 0;   // samples of the same stream addressable before `in` (set by run)
     void launch(Counters &c, cudaStream_t st, bool wn, const float2 *in, float2 *out, long long n, int Ls, int Ws, int nseg,
                 int n_work, int ncp, int mode, long long in_stride, long long out_stride)
     {
@@ -333,7 +334,8 @@ template <class LOOP> struct SegStage {
             const int grid = (n_work + WN_WARPS - 1) / WN_WARPS;
             XRD_LAUNCH(c, (wn_loop_kernel<LOOP, WN_K>), grid, WN_WARPS * 32, wn_smem_bytes<WN_K>(), st, in, out, n, Ls, Ws, nseg,
                        n_work, d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(),
-                       d_ckpt.as<State>(), ncp, WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride);
+                       d_ckpt.as<State>(), ncp, WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride,
+                       hist);
         } else {
             const int grid = (n_work + SEG_NTH - 1) / SEG_NTH;
             XRD_LAUNCH(c, (seg_loop_kernel<LOOP, SEG_TS>), grid, SEG_NTH, 0, st, in, out, n, Ls, Ws, nseg, n_work,
@@ -342,11 +344,14 @@ template <class LOOP> struct SegStage {
         }
     }
 
+    // hist_avail: samples of the same stream that are still in place right before `in` (an earlier piece of the
+    // same call); speculative warm-ups of the window kernel may start there instead of at in[0]
     void run(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n, long long in_stride,
-             long long out_stride)
+             long long out_stride, long long hist_avail = 0)
     {
         if (n <= 0) return;
         const bool wn = use_wn;
+        hist = wn ? hist_avail : 0;
         int Ls, Ws;
         if (wn) {
             long long l = Lw;
@@ -382,7 +387,7 @@ template <class LOOP> struct SegStage {
                 dim3 g2(nseg, nch);
                 XRD_LAUNCH(c, costas_seg_advance_kernel, g2, 256, 0, st, d_psi.as<float>(), d_adv.as<float>(), nseg, Ls / CPB,
                            nblk, nblk);
-                resolve(c, st, nseg, Ls, Ws);
+                resolve(c, st, nseg, Ls, (long long)Ws - hist);
                 launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 3, in_stride, out_stride);
             } else {
                 launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 0, in_stride, out_stride);
@@ -665,6 +670,8 @@ struct xrd_demod {
     ~xrd_demod()
     {
         if (h_pin) cudaFreeHost(h_pin);
+        for (auto e : piece_ev) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
     long long in_stride() const { return cap_n + dec.hist(); }
@@ -748,19 +755,13 @@ struct xrd_demod {
         for (auto &f : fifo) f.head = f.count = 0;
     }
 
-    // iq_dev: [nch][n] samples of `type` on the device.  sym_dev: [nch][cap].
-    int run_device(const void *iq_dev, long long n, int type, float2 *sym_dev, long long cap, int64_t *counts)
+    // Front half of the chain (everything at the sample rate: ingest, decimator, AGC, RRC, Costas) over input
+    // samples [off, off + m) of a call whose raw input (n_total samples per channel) is iq_dev.  Pieces of one call
+    // are processed in order; off > 0 is only used with one FLOATIQ channel and no decimation, where the earlier
+    // pieces stay in place in front of this one (warm-ups reach back into them).
+    void run_front(const void *iq_dev, long long n_total, long long off, long long m, int type)
     {
-        if (n % D) {
-            err = "n_complex must be a multiple of the decimation";
-            return XRD_E_ARG;
-        }
-        if (n == 0) {
-            for (int ch = 0; ch < nch; ch++) counts[ch] = 0;
-            return XRD_OK;
-        }
-        ensure(n);
-        const long long nd = n / D;
+        const long long nd = m / D, nd_off = off / D;
         const int Hd = (D > 1) ? dec.hist() : 0, Hr = rrc.hist();
         const float2 *x = nullptr;   // AGC input, [nch] with stride xs
         long long xs = 0;
@@ -770,7 +771,7 @@ struct xrd_demod {
             const long long ds = (D > 1) ? in_stride() : nd_cap();
             for (int ch = 0; ch < nch; ch++) {
                 float *o = reinterpret_cast<float *>(dst + (size_t)ch * ds);
-                const size_t nf = (size_t)n * 2;
+                const size_t nf = (size_t)m * 2;
                 const int blocks = (int)std::min<size_t>((nf + 1023) / 1024, 148 * 16);
                 if (type == XRD_FLOATIQ) {
                     XRD_CUDA(cudaMemcpyAsync(o, (const float *)iq_dev + (size_t)ch * nf, sizeof(float) * nf,
@@ -786,42 +787,50 @@ struct xrd_demod {
             x = dst;
             xs = ds;
         } else {
-            x = (const float2 *)iq_dev;
-            xs = n;
+            x = (const float2 *)iq_dev + off;
+            xs = n_total;
         }
         if (D > 1) {
             t_dec.start(stream);
             dec.run(ctr, stream, x, b_dec.as<float2>(), nd, nch, xs, nd_cap());
-            XRD_LAUNCH(ctr, carry_prefix_kernel, nch, 256, sizeof(float2) * Hd, stream, b_in.as<float2>(), Hd, n,
+            XRD_LAUNCH(ctr, carry_prefix_kernel, nch, 256, sizeof(float2) * Hd, stream, b_in.as<float2>(), Hd, m,
                        in_stride());
             t_dec.stop(stream);
             x = b_dec.as<float2>();
             xs = nd_cap();
         }
-        float2 *agc_out = b_agc.as<float2>() + Hr;
+        float2 *agc_out = b_agc.as<float2>() + Hr + nd_off;
         t_agc.start(stream);
-        agc.run(ctr, stream, x, agc_out, nd, xs, agc_stride());
+        agc.run(ctr, stream, x, agc_out, nd, xs, agc_stride(), nd_off);
         t_agc.stop(stream);
         t_rrc.start(stream);
         // (when D == 1 and the input was converted into b_rrc, AGC has consumed it by now)
-        rrc.run(ctr, stream, agc_out, b_rrc.as<float2>(), nd, nch, agc_stride(), nd_cap());
+        rrc.run(ctr, stream, agc_out, b_rrc.as<float2>() + nd_off, nd, nch, agc_stride(), nd_cap());
+        t_rrc.stop(stream);
+        float2 *cos_out = b_cos.as<float2>() + MM_TAIL + nd_off;
+        t_cos.start(stream);
+        costas.run(ctr, stream, b_rrc.as<float2>() + nd_off, cos_out, nd, nd_cap(), cos_stride(), nd_off);
+        t_cos.stop(stream);
+        ms[0] += (D > 1) ? t_dec.ms() : 0.f;
+        ms[1] += t_agc.ms();
+        ms[2] += t_rrc.ms();
+        ms[3] += t_cos.ms();
+    }
+
+    // Back half: M&M over the Costas output of the whole call, history carries, totals
+    int run_back(long long n, float2 *sym_dev, long long cap, int64_t *counts)
+    {
+        const long long nd = n / D;
+        const int Hr = rrc.hist();
         XRD_LAUNCH(ctr, carry_prefix_kernel, nch, 256, sizeof(float2) * Hr, stream, b_agc.as<float2>(), Hr, nd,
                    agc_stride());
-        t_rrc.stop(stream);
         float2 *cos_out = b_cos.as<float2>() + MM_TAIL;
-        t_cos.start(stream);
-        costas.run(ctr, stream, b_rrc.as<float2>(), cos_out, nd, nd_cap(), cos_stride());
-        t_cos.stop(stream);
         t_mm.start(stream);
         int rc = mm.run(ctr, stream, cos_out, sym_dev, nd, cap, cos_stride(), cap, counts);
         XRD_LAUNCH(ctr, carry_prefix_kernel, nch, 32, sizeof(float2) * MM_TAIL, stream, b_cos.as<float2>(), MM_TAIL, nd,
                    cos_stride());
         t_mm.stop(stream);
         XRD_CUDA(cudaStreamSynchronize(stream));
-        ms[0] = (D > 1) ? t_dec.ms() : 0.f;
-        ms[1] = t_agc.ms();
-        ms[2] = t_rrc.ms();
-        ms[3] = t_cos.ms();
         ms[4] = t_mm.ms();
         for (int ch = 0; ch < nch; ch++) {
             n_in[ch] += (uint64_t)n;
@@ -830,6 +839,81 @@ struct xrd_demod {
         if (rc == XRD_E_OVERFLOW) err = "symbol output capacity too small";
         return rc;
     }
+
+    bool check_len(long long n, int64_t *counts, int &rc)
+    {
+        if (n % D) {
+            err = "n_complex must be a multiple of the decimation";
+            rc = XRD_E_ARG;
+            return false;
+        }
+        if (n == 0) {
+            for (int ch = 0; ch < nch; ch++) counts[ch] = 0;
+            rc = XRD_OK;
+            return false;
+        }
+        return true;
+    }
+
+    // iq_dev: [nch][n] samples of `type` on the device.  sym_dev: [nch][cap].
+    int run_device(const void *iq_dev, long long n, int type, float2 *sym_dev, long long cap, int64_t *counts)
+    {
+        int rc = XRD_OK;
+        if (!check_len(n, counts, rc)) return rc;
+        ensure(n);
+        for (float &v : ms) v = 0.f;
+        run_front(iq_dev, n, 0, n, type);
+        return run_back(n, sym_dev, cap, counts);
+    }
+
+    // Host input: the H2D copy is cut into pieces and the front half of the chain runs on every piece as it lands
+    // (copy engine and SMs overlap); M&M runs once over the whole call.  Pieces are only used where earlier pieces
+    // stay in place for the warm-ups of later ones (one FLOATIQ channel, no decimation) and the call is long.
+    int run_host(const void *iq, long long n, int type, float2 *sym_dev, long long cap, int64_t *counts)
+    {
+        int rc = XRD_OK;
+        if (!check_len(n, counts, rc)) return rc;
+        const size_t sb = (type == XRD_FLOATIQ) ? 8 : (type == XRD_S16IQ ? 4 : 2);
+        b_raw.ensure(sb * (size_t)n * nch);
+        ensure(n);
+        for (float &v : ms) v = 0.f;
+        int pieces = 1;
+        if (type == XRD_FLOATIQ && D == 1 && nch == 1 && piece_min > 0) pieces = (int)std::min<long long>(max_pieces, n / piece_min);
+        if (pieces <= 1) {
+            XRD_CUDA(cudaMemcpyAsync(b_raw.p, iq, sb * (size_t)n * nch, cudaMemcpyHostToDevice, stream));
+            run_front(b_raw.p, n, 0, n, type);
+            return run_back(n, sym_dev, cap, counts);
+        }
+        if (!copy_stream) XRD_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        while ((int)piece_ev.size() < pieces) {
+            cudaEvent_t e;
+            XRD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            piece_ev.push_back(e);
+        }
+        // piece boundaries on checkpoint multiples so that segments tile every piece the same way
+        const long long step = ((n + pieces - 1) / pieces + WN_CKPT - 1) / WN_CKPT * WN_CKPT;
+        // the copies must not start before earlier work on the compute stream is done with b_raw
+        XRD_CUDA(cudaEventRecord(piece_ev[0], stream));
+        XRD_CUDA(cudaStreamWaitEvent(copy_stream, piece_ev[0], 0));
+        int np = 0;
+        for (long long off = 0; off < n; off += step, np++) {
+            const long long m = std::min(step, n - off);
+            XRD_CUDA(cudaMemcpyAsync((char *)b_raw.p + sb * off, (const char *)iq + sb * off, sb * (size_t)m,
+                                     cudaMemcpyHostToDevice, copy_stream));
+            XRD_CUDA(cudaEventRecord(piece_ev[np], copy_stream));
+        }
+        np = 0;
+        for (long long off = 0; off < n; off += step, np++) {
+            const long long m = std::min(step, n - off);
+            XRD_CUDA(cudaStreamWaitEvent(stream, piece_ev[np], 0));
+            run_front(b_raw.p, n, off, m, type);
+        }
+        return run_back(n, sym_dev, cap, counts);
+    }
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> piece_ev;
+    long long piece_min = 16000000;   // samples; 0 disables the pieces
+    int max_pieces = 2;             // more pieces shorten the Costas segments and cost more re-run rounds than the overlap wins
 };
 
 static size_t type_bytes(int type)
@@ -996,11 +1080,8 @@ int xrd_demod_batch(xrd_demod *d, const void *iq, size_t n_complex, int type, fl
     if (!d || !iq || !sym_out || !n_sym || !type_bytes(type)) return XRD_E_ARG;
     return guarded(&d->err, [&]() {
         XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
-        const size_t in_bytes = type_bytes(type) * n_complex * d->nch;
-        d->b_raw.ensure(in_bytes);
         d->b_sym.ensure(sizeof(float2) * cap * d->nch);
-        XRD_CUDA(cudaMemcpyAsync(d->b_raw.p, iq, in_bytes, cudaMemcpyHostToDevice, d->stream));
-        int rc = d->run_device(d->b_raw.p, (long long)n_complex, type, d->b_sym.as<float2>(), (long long)cap, n_sym);
+        int rc = d->run_host(iq, (long long)n_complex, type, d->b_sym.as<float2>(), (long long)cap, n_sym);
         if (rc != XRD_OK && rc != XRD_E_OVERFLOW) return rc;
         for (int ch = 0; ch < d->nch; ch++) {
             const size_t cnt = (size_t)std::min<long long>(n_sym[ch], (long long)cap);
@@ -1155,6 +1236,8 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
     if (t->mm_lanes) d->mm.nt = t->mm_lanes & 0xffff;
     d->mm.force64 = (t->mm_lanes & 0x10000) != 0;
     if (t->mm_warm) d->mm.W = t->mm_warm;
+    if (t->h2d_pieces < 0) return XRD_E_ARG;
+    if (t->h2d_pieces) d->max_pieces = t->h2d_pieces;
     return XRD_OK;
 }
 

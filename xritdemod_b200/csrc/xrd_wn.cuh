@@ -334,7 +334,7 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
                typename LOOP::State *__restrict__ entry, typename LOOP::State *__restrict__ exit_,
                const typename LOOP::State *__restrict__ carried, const int *__restrict__ list,
                typename LOOP::State *__restrict__ ckpt, int ncp, int C, unsigned long long *__restrict__ iters_total,
-               typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride)
+               typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride, long long hist)
 {
     extern __shared__ __align__(16) unsigned char wn_smem[];
     typedef typename LOOP::State State;
@@ -353,7 +353,8 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
     State st;
     if (mode == 0 || mode == 2) {
         // speculative warm-up: the state at the segment start (mode 2 stops there)
-        const bool from_carried = (j == 0 || seg0 - W <= 0);
+        // `hist` samples of this stream before in[0] are still in place (earlier piece of the same call): warm-ups may use them
+        const bool from_carried = (j == 0 || seg0 - W + hist <= 0);
         int s_begin;
         if (from_carried) {
             st = carried[ch];
@@ -463,7 +464,8 @@ costas_seg_advance_kernel(const float *__restrict__ psi, float *__restrict__ adv
 }
 
 // puts the warm-up entry states of a channel on the branch of segment 0 (which starts from the exact state)
-__global__ void costas_resolve_kernel(int nseg, int L, int W, CostasState *__restrict__ entry, const float *__restrict__ adv,
+__global__ void costas_resolve_kernel(int nseg, int L, long long W /* warm-up minus addressable history */,
+                                      CostasState *__restrict__ entry, const float *__restrict__ adv,
                                       int *__restrict__ n_flipped)
 {
     // flip[j] = entry j lies on the other branch than (entry j-1 advanced by adv[j-1]) -- independent of what

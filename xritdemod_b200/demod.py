@@ -61,7 +61,7 @@ class LoopState(C.Structure):
 class Tuning(C.Structure):
     _fields_ = [
         ("agc_seg", C.c_int32), ("agc_warm", C.c_int32), ("costas_seg", C.c_int32), ("costas_warm", C.c_int32),
-        ("mm_seg", C.c_int64), ("mm_warm", C.c_int64), ("mm_lanes", C.c_int32), ("loop_kernel", C.c_int32),
+        ("mm_seg", C.c_int64), ("mm_warm", C.c_int64), ("mm_lanes", C.c_int32), ("loop_kernel", C.c_int32), ("h2d_pieces", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
