@@ -130,9 +130,10 @@ typedef struct {
     int64_t mm_seg, mm_warm;
     int32_t mm_lanes;            /* symbols per fixed-point window of the M&M chain kernel: 128/256/512/1024
                                     (+0x10000: force the generic 64-bit kernel; tests) */
-    int32_t loop_kernel;         /* AGC/Costas kernel: 0 default, 1 one thread per segment, 2 window-Newton warp chains */
+    int32_t loop_kernel;         /* AGC/Costas kernel: 0 default, 1 one thread per segment, 2 window-Newton warp chains,
+                                    3..6 window-Newton CTA chains with (slots per thread, warps) = (1,4) (2,4) (1,2) (2,2) */
     int32_t h2d_pieces;          /* host-input calls: copy/compute pieces (0 default = up to 2 of >= 16 M samples, 1 = one copy) */
-    int32_t reserved;
+    int32_t reserved;            /* tuning experiments: chains per SM, Costas | AGC << 8 (0 keeps defaults) */
 } xrd_tuning;
 int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t);
 

@@ -275,6 +275,8 @@ template <class LOOP> struct SegStage {
     // segments as the device holds chains (chains_per_sm warps per SM), at least Lw_min samples each
     int Lw = 0, Ww = 16384, Lw_min = 16384, chains_per_sm = 8;
     bool use_wn = true;
+    int wn_variant = 2;   // 2: one warp per chain (K = 4); 3..7: one CTA per chain, (K, warps) = (1,4) (2,4) (1,2) (2,2) (2,8)
+    int redo_variant = 4; // kernel of the certified re-runs: few chains, so the widest window (fastest single chain) wins
     bool use_mirror = false;
     int nch = 1, sm_count = 148;
     DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list, d_ckpt, d_iters, d_psi, d_adv;
@@ -330,7 +332,20 @@ template <class LOOP> struct SegStage {
     void launch(Counters &c, cudaStream_t st, bool wn, const float2 *in, float2 *out, long long n, int Ls, int Ws, int nseg,
                 int n_work, int ncp, int mode, long long in_stride, long long out_stride)
     {
-        if (wn) {
+        const int variant = (mode == 1) ? redo_variant : wn_variant;
+        if (wn && variant >= 3) {
+            // one CTA of WPC warps per chain (wn_cta_kernel<LOOP, K, WPC>)
+#define XRD_WN_CTA(KV, WV)                                                                                              \
+    XRD_LAUNCH(c, (wn_cta_kernel<LOOP, KV, WV>), n_work, 32 * WV, 0, st, in, out, n, Ls, Ws, nseg, n_work,              \
+               d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(), d_ckpt.as<State>(), ncp, \
+               WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride, hist)
+            if (variant == 3) XRD_WN_CTA(1, 4);
+            else if (variant == 4) XRD_WN_CTA(2, 4);
+            else if (variant == 5) XRD_WN_CTA(1, 2);
+            else if (variant == 6) XRD_WN_CTA(2, 2);
+            else XRD_WN_CTA(2, 8);
+#undef XRD_WN_CTA
+        } else if (wn) {
             const int grid = (n_work + WN_WARPS - 1) / WN_WARPS;
             XRD_LAUNCH(c, (wn_loop_kernel<LOOP, WN_K>), grid, WN_WARPS * 32, wn_smem_bytes<WN_K>(), st, in, out, n, Ls, Ws, nseg,
                        n_work, d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(),
@@ -1228,10 +1243,14 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
     if (t->costas_seg) d->costas.L = d->costas.Lw = t->costas_seg;
     if (t->costas_warm) d->costas.W = d->costas.Ww = t->costas_warm;
     if (t->loop_kernel == 1) d->agc.use_wn = d->costas.use_wn = false;
-    else if (t->loop_kernel == 2) {
+    else if ((t->loop_kernel & 0xff) >= 2 && (t->loop_kernel & 0xff) <= 7 && (t->loop_kernel >> 8) <= 7) {
         d->agc.use_wn = agc_wn_ok(d->agc.prm.max_gain);
         d->costas.use_wn = costas_wn_ok(d->costas.prm);
-    }
+        d->agc.wn_variant = d->costas.wn_variant = t->loop_kernel & 0xff;
+        d->agc.redo_variant = d->costas.redo_variant = (t->loop_kernel >> 8) ? (t->loop_kernel >> 8) : (t->loop_kernel & 0xff);
+    } else if (t->loop_kernel) return XRD_E_ARG;
+    if (t->reserved > 0) d->costas.chains_per_sm = t->reserved & 0xff;
+    if ((t->reserved >> 8) > 0) d->agc.chains_per_sm = (t->reserved >> 8) & 0xff;
     if (t->mm_seg) d->mm.L = std::max<long long>(t->mm_seg, 64);
     if (t->mm_lanes) d->mm.nt = t->mm_lanes & 0xffff;
     d->mm.force64 = (t->mm_lanes & 0x10000) != 0;
@@ -1491,10 +1510,11 @@ int xrd_stage_set_tuning(xrd_stage *s, int64_t seg, int64_t warm)
 
 int xrd_stage_set_loop_kernel(xrd_stage *s, int kernel)
 {
-    if (!s || kernel < 0 || kernel > 2) return XRD_E_ARG;
+    if (!s || kernel < 0 || kernel > 7) return XRD_E_ARG;
     const bool wn = kernel != 1;
     if (s->kind == xrd_stage::AGC) s->agc.use_wn = wn && agc_wn_ok(s->agc.prm.max_gain);
     if (s->kind == xrd_stage::COSTAS) s->costas.use_wn = wn && costas_wn_ok(s->costas.prm);
+    if (kernel >= 2) s->agc.wn_variant = s->costas.wn_variant = s->agc.redo_variant = s->costas.redo_variant = kernel;
     return XRD_OK;
 }
 

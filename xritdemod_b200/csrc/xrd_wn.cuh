@@ -384,6 +384,305 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
 
 
 // ---------------------------------------------------------------------------------------
+// The same chain run by a whole CTA: WPC warps share one window of NT = 32 * WPC * K samples
+// (thread t holds slots t*K .. t*K+K-1).  A chain advances NT-lane iterations whose length is set by
+// the dependent latency of one literal step plus a scan, so spreading the window over more warps
+// (K = 1) makes the single chain ~3x faster -- which is what bounds the certified re-run rounds
+// (few chains, each as long as its merge time) -- and puts 4x the warps on an SM for the same
+// number of segments.  Two CTA barriers per iteration; everything exchanged between threads goes
+// through double-buffered shared memory and every thread derives the (uniform) control state itself.
+// ---------------------------------------------------------------------------------------
+template <class LOOP, int K, int WPC> struct WnCta {
+    typedef typename LOOP::State State;
+    static constexpr int T = 32 * WPC;        // threads
+    static constexpr int NT = T * K;          // slots
+    static constexpr int RS = 4 * NT;         // ring samples
+    static constexpr int NS = WnOf<LOOP>::type::NS;
+    struct Shared {
+        float2 ring[RS];
+        State o[2][NT];            // literal step results of every slot
+        double tot[2][WPC][NS];    // warp totals of the differences
+        double bex[2][NS];         // in-warp exclusive prefix of the base thread
+        int bad[2][WPC];           // first unaccepted rank seen by each warp
+    };
+};
+
+template <class LOOP, int K, int WPC, bool WRITE, int CK>
+__device__ __forceinline__ typename LOOP::State
+wn_run_cta(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, int s_end, typename LOOP::State st,
+           const typename LOOP::Params &prm, typename WnCta<LOOP, K, WPC>::Shared &sh, typename LOOP::State *ck, int C,
+           bool *merged, unsigned long long *iters_out)
+{
+    typedef typename LOOP::State State;
+    typedef typename WnOf<LOOP>::type WN;
+    typedef WnCta<LOOP, K, WPC> G;
+    constexpr int NS = G::NS, T = G::T, NT = G::NT, RS = G::RS, MARGIN = 2 * NT;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+
+    int base = s_begin, tbt = 0, par = 0;   // tbt: thread that holds the base slot (its slot 0)
+    State bs[K];
+    float2 xs[K];
+    double basew[NS];
+    WN::widen(st, basew);
+    State base_state = st;
+    State *pend_slot = nullptr;   // checkpoint write deferred past the next barrier (thread 0)
+    State pend_val = st;
+
+    int fill = s_begin;
+    {
+        const int target = min(s_begin + NT + MARGIN, s_end);
+        for (int i = fill + t; i < target; i += T) cp_async8(&sh.ring[i & (RS - 1)], x + i);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        fill = max(fill, target);
+        cp_async_wait_all();
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int r = t * K + k;
+        double f[NS];
+        WN::extrapolate(basew, r, f);
+        WN::normalise(f);
+        bs[k] = (r == 0) ? st : WN::narrow(f);
+        const int i = base + r;
+        xs[k] = (i < s_end) ? sh.ring[i & (RS - 1)] : make_float2(0.f, 0.f);
+    }
+    unsigned long long iters = 0;
+    bool done_merged = false;
+
+    while (base < s_end) {
+        iters++;
+        // ---- 1. literal step of every slot, exact differences, in-warp scan
+        State o[K];
+        float2 yo[K];
+        double li[K][NS];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            o[k] = bs[k];
+            yo[k] = LOOP::step_sel(o[k], prm, xs[k]);
+            sh.o[par][t * K + k] = o[k];
+            double fo[NS], fs[NS];
+            WN::widen(o[k], fo);
+            WN::widen(bs[k], fs);
+#pragma unroll
+            for (int c = 0; c < NS; c++) li[k][c] = k ? li[k - 1][c] + (fo[c] - fs[c]) : (fo[c] - fs[c]);
+        }
+        double we[NS];
+#pragma unroll
+        for (int c = 0; c < NS; c++) {
+            double v = li[K - 1][c];
+#pragma unroll
+            for (int ofs = 1; ofs < 32; ofs <<= 1) {
+                const double a = __shfl_up_sync(0xffffffffu, v, ofs);
+                if (lane >= ofs) v += a;
+            }
+            we[c] = v - li[K - 1][c];
+            if (lane == 31) sh.tot[par][wid][c] = v;
+            if (t == tbt) sh.bex[par][c] = we[c];
+        }
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // ring samples the freed slots will need (see wn_run)
+        __syncthreads();   // B1
+        if (t == 0 && pend_slot) {
+            *pend_slot = pend_val;
+            pend_slot = nullptr;
+        }
+        // ---- 2. state before this thread's slot 0 if all before it is true; acceptance
+        double total[NS], lanebase[NS];
+        {
+            const int wb = tbt >> 5;
+#pragma unroll
+            for (int c = 0; c < NS; c++) {
+                double pre = 0.0, preb = 0.0, tt = 0.0;
+#pragma unroll
+                for (int q = 0; q < WPC; q++) {
+                    const double v = sh.tot[par][q][c];
+                    if (q < wid) pre += v;
+                    if (q < wb) preb += v;
+                    tt += v;
+                }
+                total[c] = tt;
+                const double e = (pre + we[c]) - (preb + sh.bex[par][c]);
+                lanebase[c] = basew[c] + ((t < tbt) ? e + tt : e);
+            }
+        }
+        State prev[K];
+        prev[0] = sh.o[par][(t * K + NT - 1) & (NT - 1)];
+#pragma unroll
+        for (int k = 1; k < K; k++) prev[k] = o[k - 1];
+        const int lr = ((t - tbt) & (T - 1)) * K;
+        unsigned mybad = NT;
+#pragma unroll
+        for (int k = K - 1; k >= 1; k--)
+            if (!LOOP::same(bs[k], prev[k])) mybad = lr + k;
+        if (lr != 0 && !LOOP::same(bs[0], prev[0])) mybad = lr;
+        mybad = __reduce_min_sync(0xffffffffu, mybad);
+        if (lane == 0) sh.bad[par][wid] = (int)mybad;
+        __syncthreads();   // B2
+        int A = s_end - base;
+#pragma unroll
+        for (int q = 0; q < WPC; q++) A = min(A, sh.bad[par][q]);
+        if (base + A >= s_end) {
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (WRITE && lr + k < A) y[base + lr + k] = yo[k];
+            base_state = sh.o[par][(tbt * K + A - 1) & (NT - 1)];
+            base += A;
+            break;
+        }
+        const int Ap = A & ~(K - 1);
+        const bool freed = lr < Ap;
+        if (Ap) {
+            if (WRITE && freed) {
+#pragma unroll
+                for (int k = 0; k < K; k++) y[base + lr + k] = yo[k];
+            }
+            const State nb = sh.o[par][(tbt * K + Ap - 1) & (NT - 1)];
+            if (CK != WN_CK_NONE) {
+                const int i0 = (base + Ap) & ~(C - 1);
+                if (i0 > base && i0 > 0 && i0 < s_end) {
+                    const State cs = sh.o[par][(tbt * K + (i0 - base) - 1) & (NT - 1)];   // state before sample i0
+                    State *slot = ck + (i0 >> (31 - __clz(C)));
+                    if (CK == WN_CK_COMPARE && LOOP::same(*slot, cs)) {   // every thread reads the same words
+                        done_merged = true;
+                        break;
+                    }
+                    if (t == 0) {
+                        pend_slot = slot;   // written after the next barrier: nobody may still be reading it
+                        pend_val = cs;
+                    }
+                }
+            }
+            base_state = nb;
+        }
+        // ---- 3. next believed states
+        double pb[NS];
+#pragma unroll
+        for (int c = 0; c < NS; c++) pb[c] = lanebase[c];
+        if (freed) {
+            double endw[NS];
+#pragma unroll
+            for (int c = 0; c < NS; c++) endw[c] = basew[c] + total[c];
+            WN::extrapolate(endw, lr, pb);
+#pragma unroll
+            for (int k = 0; k < K - 1; k++) {
+                if (NS > 1) {
+                    double z[NS], e[NS];
+#pragma unroll
+                    for (int c = 0; c < NS; c++) z[c] = (c == NS - 1) ? endw[c] : 0.0;
+                    WN::extrapolate(z, k + 1, e);
+                    li[k][0] = e[0];
+                    li[k][NS - 1] = 0.0;
+                } else {
+                    li[k][0] = 0.0;
+                }
+            }
+            const int i0 = base + NT + lr;
+#pragma unroll
+            for (int k = 0; k < K; k++) xs[k] = (i0 + k < s_end) ? sh.ring[(i0 & (RS - 1)) + k] : make_float2(0.f, 0.f);
+        }
+        bool odd = false;
+        State nbs[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double f[NS];
+#pragma unroll
+            for (int c = 0; c < NS; c++) f[c] = k ? pb[c] + li[k - 1][c] : pb[c];
+            nbs[k] = WN::narrow(f);
+            odd |= !WN::in_range(nbs[k]);
+        }
+        if (!freed && lr <= A) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (lr + k < A) nbs[k] = bs[k];
+                else if (lr + k == A) nbs[k] = prev[k];
+            }
+        }
+        if (odd) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (!WN::in_range(nbs[k])) {
+                    double f[NS];
+#pragma unroll
+                    for (int c = 0; c < NS; c++) f[c] = k ? pb[c] + li[k - 1][c] : pb[c];
+                    WN::normalise(f);
+                    nbs[k] = WN::narrow(f);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) bs[k] = nbs[k];
+        if (Ap) {
+            WN::widen(base_state, basew);
+            tbt = (tbt + Ap / K) & (T - 1);
+            base += Ap;
+            const int target = min(base + NT + MARGIN, s_end);
+            for (int i = fill + t; i < target; i += T) cp_async8(&sh.ring[i & (RS - 1)], x + i);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            fill = max(fill, target);
+        }
+        par ^= 1;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (t == 0 && pend_slot) *pend_slot = pend_val;
+    if (merged) *merged = done_merged;
+    if (iters_out) *iters_out += iters;
+    return base_state;
+}
+
+// one CTA per work item; contract and modes of wn_loop_kernel
+template <class LOOP, int K, int WPC>
+__global__ void __launch_bounds__(32 * WPC)
+wn_cta_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, int L, int W, int nseg, int n_work,
+              typename LOOP::State *__restrict__ entry, typename LOOP::State *__restrict__ exit_,
+              const typename LOOP::State *__restrict__ carried, const int *__restrict__ list,
+              typename LOOP::State *__restrict__ ckpt, int ncp, int C, unsigned long long *__restrict__ iters_total,
+              typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride, long long hist)
+{
+    typedef typename LOOP::State State;
+    __shared__ __align__(16) typename WnCta<LOOP, K, WPC>::Shared sh;
+    const int w = blockIdx.x;
+    if (w >= n_work) return;
+    const int g = (mode == 1) ? list[w] : w;
+    const int ch = g / nseg, j = g - ch * nseg;
+    const long long seg0 = (long long)j * L;
+    const int len = (int)min((long long)L, n - seg0);
+    const float2 *x = in + (size_t)ch * in_ch_stride + seg0;
+    float2 *y = out + (size_t)ch * out_ch_stride + seg0;
+    State *ck = ckpt + (size_t)g * ncp;
+    unsigned long long iters = 0;
+    State st;
+    if (mode == 0 || mode == 2) {
+        const bool from_carried = (j == 0 || seg0 - W + hist <= 0);
+        int s_begin;
+        if (from_carried) {
+            st = carried[ch];
+            s_begin = (int)-seg0;
+        } else {
+            s_begin = -W;
+            float2 first[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) first[i] = __ldg(x + s_begin + i);
+            st = LOOP::guess(prm, first, 16);
+        }
+        if (s_begin < 0)
+            st = wn_run_cta<LOOP, K, WPC, false, WN_CK_NONE>(x, y, s_begin, 0, st, prm, sh, nullptr, C, nullptr, &iters);
+        if (threadIdx.x == 0) entry[g] = st;
+    }
+    if (mode == 3) st = entry[g];
+    if (mode == 0 || mode == 3) {
+        st = wn_run_cta<LOOP, K, WPC, true, WN_CK_RECORD>(x, y, 0, len, st, prm, sh, ck, C, nullptr, &iters);
+        if (threadIdx.x == 0) exit_[g] = st;
+    } else if (mode == 1) {
+        st = entry[g];
+        bool merged = false;
+        st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE>(x, y, 0, len, st, prm, sh, ck, C, &merged, &iters);
+        if (threadIdx.x == 0 && !merged) exit_[g] = st;
+    }
+    if (threadIdx.x == 0 && iters_total) atomicAdd(iters_total, iters);
+}
+
+// ---------------------------------------------------------------------------------------
 // Costas: which of the two stable lock points (carrier phase, carrier phase + pi) a cold warm-up
 // ends on is a coin flip, and a segment run on the wrong one has to be re-run in full.  The
 // carrier phase itself is observable without the loop: arg(sum x^2) over a short block is twice
