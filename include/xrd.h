@@ -128,8 +128,9 @@ typedef struct {
     int32_t agc_seg, agc_warm;
     int32_t costas_seg, costas_warm;
     int64_t mm_seg, mm_warm;
-    int32_t mm_lanes;            /* symbols per fixed-point window of the M&M chain kernel: 128/256/512/1024
-                                    (+0x10000: force the generic 64-bit kernel; tests) */
+    int32_t mm_lanes;            /* M&M chain kernel (tests/tuning): 0 default (mm_chain32_kernel, 1024 lanes); 128/256/512/1024 =
+                                    mm_chain32_kernel with that many lanes (+0x10000: the generic 64-bit kernel);
+                                    0x20000 + (slots per thread << 8) + warps = window-Newton chain of that shape */
     int32_t loop_kernel;         /* AGC/Costas kernel: 0 default, 1 one thread per segment, 2 window-Newton warp chains,
                                     3..6 window-Newton CTA chains with (slots per thread, warps) = (1,4) (2,4) (1,2) (2,2) */
     int32_t h2d_pieces;          /* host-input calls: copy/compute pieces (0 default = up to 2 of >= 16 M samples, 1 = one copy) */

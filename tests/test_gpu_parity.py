@@ -144,6 +144,21 @@ def test_costas_branch_resolution_over_carrier_offsets(gpu, xrd, oracle, df_hz, 
     assert_bitexact(c.Work(taps["rrc"]), taps["costas"], "Costas, df %g Hz" % df_hz)
 
 
+@pytest.mark.parametrize("lanes", [256, 1024, 0x10000 + 256, 0x20000 + (2 << 8) + 16, 0x20000 + (4 << 8) + 8, 0x20000 + (1 << 8) + 16])
+@pytest.mark.parametrize("mode", ["hrit", "lrit"])
+def test_mm_chain_kernels_agree(gpu, xrd, oracle, mode, lanes):
+    """every M&M chain kernel (32-bit fixed point, generic 64-bit, window-Newton shapes) gives the oracle's symbols,
+    with segments short enough to need certified re-runs"""
+    _, x = make_signal(mode, 1 << 21)
+    ref = oracle.Chain(oracle.config(mode == "hrit")).process(x)
+    d = xrd.Demodulator(mode=mode)
+    d.set_tuning(mm_lanes=lanes, mm_seg=150000, mm_warm=60000)
+    half = len(x) // 2 + 12345
+    got = np.concatenate([d.demod(x[:half]), d.demod(x[half:])])
+    check_symbols(got, ref, "M&M kernel %#x" % lanes)
+    assert d.stats()["mm_redo"] > 0
+
+
 # ------------------------------------------------------------------ the chain (processSamples)
 @pytest.mark.parametrize("mode,n", [("lrit", 1 << 20), ("hrit", 1 << 22)])
 def test_chain_one_shot(gpu, xrd, oracle, mode, n):

@@ -4,6 +4,7 @@
 #include "../../include/xrd.h"
 #include "xrd_kernels.cuh"
 #include "xrd_wn.cuh"
+#include "xrd_mmwn.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -471,7 +472,9 @@ struct MmStage {
     MmParams prm;
     long long L = 0, W = 800000;    // L == 0: one segment per SM (set per call); W: speculative warm-up (samples)
     long long Lmin = 262144;
-    int nt = 0;                     // lanes per chain (0 = auto)
+    int nt = 0;                     // lanes per chain of mm_chain32_kernel (0 = auto)
+    int wn_k = 0, wn_wpc = 16;      // window-Newton chain kernel (xrd_mmwn.cuh): slots per thread, warps; 0 = mm_chain32_kernel,
+                                    // which is still ~7 % faster on B200 (fewer, cheaper instructions per symbol)
     bool force64 = false;           // tests: always use the generic 64-bit chain kernel
     int sm_count = 148;
     int nch = 1;
@@ -526,6 +529,32 @@ struct MmStage {
         const double dev_max = (double)NT * prm.gain_omega + prm.gain_mu;
         const bool fast = !force64 && n < (1LL << 30) && Lseg < (1LL << 30) && W < (1LL << 30) && cap_seg < (1LL << 30) &&
                           32.0 * dev_max < 0.45 && 2.0 * prm.omega_lim + prm.gain_mu < 0.45 && prm.omega_mid < 1024.f;
+        if (fast && wn_k > 0) {
+            // window-Newton chain: K slots per thread, WPC warps (xrd_mmwn.cuh)
+            const int NTw = 32 * wn_wpc * wn_k;
+            int Rw = next_pow2((long long)(2 * NTw * adv) + 160);
+            const MmWnLayout lay(NTw, wn_wpc, Rw);
+            if (lay.total <= 220 * 1024) {
+                const int ncp = (int)(Lseg / ck_spacing) + 2;
+                d_ckpt.ensure(sizeof(MmCk) * (size_t)grid.x * grid.y * ncp);
+#define XRD_MM_WN(KV, WV)                                                                                                \
+    do {                                                                                                                 \
+        XRD_CUDA(cudaFuncSetAttribute(mm_wn_kernel<KV, WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total)); \
+        XRD_LAUNCH(c, (mm_wn_kernel<KV, WV>), grid, 32 * WV, lay.total, st, in, d_stage.as<float2>(), (int)n, (int)Lseg,  \
+                   (int)W, nseg, (int)cap_seg, d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(),     \
+                   d_redo.as<unsigned char>(), d_segout.as<MmSegOut>(), d_table.as<float>(), prm, mode, in_stride,       \
+                   stage_stride, Rw, d_ckpt.as<MmCk>(), ncp, ck_spacing);                                                \
+    } while (0)
+                if (wn_k == 2 && wn_wpc == 16) XRD_MM_WN(2, 16);
+                else if (wn_k == 4 && wn_wpc == 8) XRD_MM_WN(4, 8);
+                else if (wn_k == 4 && wn_wpc == 16) XRD_MM_WN(4, 16);
+                else if (wn_k == 2 && wn_wpc == 8) XRD_MM_WN(2, 8);
+                else if (wn_k == 1 && wn_wpc == 32) XRD_MM_WN(1, 32);
+                else XRD_MM_WN(1, 16);
+#undef XRD_MM_WN
+                return;
+            }
+        }
         if (fast) {
             const size_t smem32 = mm_chain32_smem_bytes(NT, R);
             const int ncp = (int)(Lseg / ck_spacing) + 2;
@@ -1252,7 +1281,13 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
     if (t->reserved > 0) d->costas.chains_per_sm = t->reserved & 0xff;
     if ((t->reserved >> 8) > 0) d->agc.chains_per_sm = (t->reserved >> 8) & 0xff;
     if (t->mm_seg) d->mm.L = std::max<long long>(t->mm_seg, 64);
-    if (t->mm_lanes) d->mm.nt = t->mm_lanes & 0xffff;
+    if (t->mm_lanes & 0x20000) {   // window-Newton chain with (slots per thread << 8 | warps)
+        d->mm.wn_k = (t->mm_lanes >> 8) & 0xff;
+        d->mm.wn_wpc = t->mm_lanes & 0xff;
+    } else if (t->mm_lanes) {      // mm_chain32_kernel with that many lanes (+0x10000: the generic 64-bit kernel)
+        d->mm.nt = t->mm_lanes & 0xffff;
+        d->mm.wn_k = 0;
+    }
     d->mm.force64 = (t->mm_lanes & 0x10000) != 0;
     if (t->mm_warm) d->mm.W = t->mm_warm;
     if (t->h2d_pieces < 0) return XRD_E_ARG;
