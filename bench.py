@@ -152,24 +152,27 @@ def run_reference(args):
     n = 16_000_000   # bounded sample of the 125 M-sample stream (same generator, same seed)
     p = make_stream(0, N_STREAM)
     x = siggen.generate(p, n)
-    cores = 1        # the reference runs the chain of one stream on one thread (demodulator.cpp:475)
+    ncpu = os.cpu_count() or 1
+    # the arm's config is one stream per GPU; the reference runs the chain of one stream on one thread
+    # (symbolThread, demodulator.cpp:475), so N streams use N host threads (one reference process each)
+    streams = max(1, args.gpus)
+    cores = min(streams, ncpu)
     for _ in range(args.warmup):
-        cpu_oracle_msps(x)
+        cpu_oracle_msps(x, n_threads=cores)
     t = 0.0
     for _ in range(args.steps):
-        _, dt, nsym = cpu_oracle_msps(x)
+        _, dt, nsym = cpu_oracle_msps(x, n_threads=cores)
         t += dt
     ms = t / args.steps * 1e3
-    value = n / (ms * 1e-3) / 1e6
-    ncpu = os.cpu_count() or 1
+    value = cores * n / (ms * 1e-3) / 1e6
     allc, _, _ = cpu_oracle_msps(x[: 4_000_000], n_threads=ncpu)
-    sample = "first %d samples of the stream per step, 1 thread (the reference's symbolThread)" % n
+    sample = "first %d samples of %d stream(s) per step, 1 thread per stream (the reference's symbolThread)" % (n, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "HRIT BPSK 927 ksym/s, 2.5 Msps, 125000000-sample cf32 stream (configs[1])",
-                   "streams": 1, "samples_per_step": n},
+                   "streams": cores, "samples_per_step": n * cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "host_cores": ncpu, "all_cores_independent_streams_msps": allc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -231,7 +231,33 @@ struct FirStage {
             dim3 grid((unsigned)((n_out + FIR_TILE - 1) / FIR_TILE), nch);
             XRD_LAUNCH(c, fir1_kernel, grid, FIR_THREADS, smem, st, in, out, d_taps.as<float>(), ntaps, n_out, in_stride,
                        out_stride);
+        } else if (D >= 2 && D <= 5 && !force_generic) {
+#define XRD_FIR_POLY(DV)                                                                                               \
+    do {                                                                                                               \
+        const size_t smem = FirPoly<DV>::smem_bytes(ntaps);                                                            \
+        if (smem > 200 * 1024) break;                                                                                  \
+        XRD_CUDA(cudaFuncSetAttribute(fird_poly_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        dim3 grid((unsigned)((n_out + FirPoly<DV>::TILE - 1) / FirPoly<DV>::TILE), nch);                               \
+        XRD_LAUNCH(c, fird_poly_kernel<DV>, grid, FP_THREADS, smem, st, in, out, d_taps.as<float>(), ntaps, n_out,     \
+                   in_stride, out_stride);                                                                             \
+        return;                                                                                                        \
+    } while (0)
+            if (D == 2) XRD_FIR_POLY(2);
+            else if (D == 3) XRD_FIR_POLY(3);
+            else if (D == 4) XRD_FIR_POLY(4);
+            else XRD_FIR_POLY(5);
+#undef XRD_FIR_POLY
+            run_generic(c, st, in, out, n_out, nch, in_stride, out_stride);
         } else {
+            run_generic(c, st, in, out, n_out, nch, in_stride, out_stride);
+        }
+    }
+    bool force_generic = false;
+    void run_generic(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n_out, int nch, long long in_stride,
+                     long long out_stride)
+    {
+        const int tp = (ntaps + 1) & ~1;
+        {
             const size_t smem = sizeof(float) * tp + sizeof(float2) * ((size_t)(FIRD_TILE - 1) * D + 1 + ntaps - 1);
             if (smem > 48 * 1024)
                 XRD_CUDA(cudaFuncSetAttribute(fird_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

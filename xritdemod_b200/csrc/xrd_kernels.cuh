@@ -183,6 +183,92 @@ fird_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float
     }
 }
 
+// Decimating FIR, polyphase form: out[i] = sum_m sum_p h[m*D + p] * x_p[i - m] with x_p[i] = x[i*D - p].
+// Every phase is a stride-1 FIR, so the register sliding window of fir1_kernel applies per phase: a thread
+// owns R consecutive outputs and D windows of R samples; taps are still applied in the order k = 0..T-1
+// (m outer, p inner), so the result is the oracle's, bit for bit.  The tile is staged in shared memory
+// de-interleaved by phase.
+constexpr int FP_THREADS = 256;
+template <int D> struct FirPoly {
+    static constexpr int R = (D <= 4) ? 9 : ((D <= 6) ? 7 : 5);   // odd: conflict-free shared-memory stride
+    static constexpr int TILE = FP_THREADS * R;
+    __host__ __device__ static int blocks(int ntaps) { return (ntaps + D - 1) / D; }
+    __host__ __device__ static size_t smem_bytes(int ntaps)
+    {
+        const int M = blocks(ntaps);
+        return sizeof(float) * (size_t)((M * D + 1) & ~1) + sizeof(float2) * (size_t)D * (TILE + M);
+    }
+};
+
+template <int D>
+__global__ void __launch_bounds__(FP_THREADS)
+fird_poly_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float *__restrict__ taps, int ntaps,
+                 long long n_out, long long in_ch_stride, long long out_ch_stride)
+{
+    constexpr int R = FirPoly<D>::R, TILE = FirPoly<D>::TILE;
+    extern __shared__ float s_mem[];
+    const int M = FirPoly<D>::blocks(ntaps);
+    const int XL = TILE + M;                                   // samples per phase: x_p[tile0 - M .. tile0 + TILE)
+    float *s_taps = s_mem;
+    float2 *s_xp = reinterpret_cast<float2 *>(s_mem + ((M * D + 1) & ~1));
+    const int ch = blockIdx.y;
+    in += (size_t)ch * in_ch_stride;
+    out += (size_t)ch * out_ch_stride;
+    const long long tile0 = (long long)blockIdx.x * TILE;
+    const int tile_n = (int)min((long long)TILE, n_out - tile0);
+    for (int i = threadIdx.x; i < M * D; i += FP_THREADS) s_taps[i] = (i < ntaps) ? taps[i] : 0.f;
+    // stage the contiguous input span; sample g = i'*D - p goes to phase p, slot i' - (tile0 - M)
+    const long long g_lo = (tile0 - M) * D - (D - 1);
+    const long long g_hi = (tile0 + tile_n - 1) * D;            // last sample any output of the tile uses
+    const long long g_min = tile0 * D - (ntaps - 1);            // first one (older ones only meet taps >= ntaps)
+    const int span = (int)(g_hi - g_lo + 1);
+    for (int s = threadIdx.x; s < span; s += FP_THREADS) {
+        const long long g = g_lo + s;
+        // i' = ceil(g / D) for any sign of g
+        long long ip = (g >= 0) ? (g + D - 1) / D : -((-g) / D);
+        const int p = (int)(ip * D - g);
+        const int slot = (int)(ip - (tile0 - M));
+        s_xp[p * XL + slot] = (g >= g_min) ? __ldg(in + g) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const int o0 = threadIdx.x * R;
+    if (o0 >= tile_n) return;
+    float2 w[D][R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < D; p++) w[p][r] = s_xp[p * XL + o0 + r + M];
+    }
+    for (int mb = 0; mb < M; mb += R) {
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            const int m = mb + q;
+            if (m < M) {
+#pragma unroll
+                for (int p = 0; p < D; p++) {
+                    const int k = m * D + p;
+                    if (k < ntaps) {
+                        const float h = s_taps[k];
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const int sl = (r - q + R) % R;
+                            acc[r].x = fmaf(h, w[p][sl].x, acc[r].x);
+                            acc[r].y = fmaf(h, w[p][sl].y, acc[r].y);
+                        }
+                    }
+                }
+                // x_p[o0 - m - 1] enters the slot that x_p[o0 + R - 1 - m] leaves
+#pragma unroll
+                for (int p = 0; p < D; p++) w[p][(R - 1 - q) % R] = s_xp[p * XL + o0 - m - 1 + M];
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++)
+        if (o0 + r < tile_n) out[tile0 + o0 + r] = acc[r];
+}
+
 // ---------------------------------------------------------------------------------------
 // Segment-parallel feedback loops (AGC, Costas): one thread per segment.
 // ---------------------------------------------------------------------------------------
