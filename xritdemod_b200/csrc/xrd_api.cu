@@ -300,7 +300,7 @@ template <class LOOP> struct SegStage {
     int L = 4096, W = 32768;
     // window-Newton kernel (wn_loop_kernel): one warp per segment, long segments.  Lw == 0: as many
     // segments as the device holds chains (chains_per_sm warps per SM), at least Lw_min samples each
-    int Lw = 0, Ww = 16384, Lw_min = 16384, chains_per_sm = 8;
+    int Lw = 0, Ww = 16384, Lw_min = 16384, chains_per_sm = 8, chains_per_sm_max = 16;
     bool use_wn = true;
     int wn_variant = 2;   // 2: one warp per chain (K = 4); 3..7: one CTA per chain, (K, warps) = (1,4) (2,4) (1,2) (2,2) (2,8)
     int redo_variant = 4; // kernel of the certified re-runs: few chains, so the widest window (fastest single chain) wins
@@ -398,7 +398,11 @@ template <class LOOP> struct SegStage {
         if (wn) {
             long long l = Lw;
             if (l <= 0) {
-                const int per_ch = std::max(1, sm_count * chains_per_sm / nch);
+                // more chains per SM when the call is large enough to keep them long (many channels)
+                int cps = chains_per_sm;
+                if (chains_per_sm_max > cps)
+                    cps = (int)std::min<long long>(chains_per_sm_max, std::max<long long>(cps, n * nch / 100000 / sm_count));
+                const int per_ch = std::max(1, sm_count * cps / nch);
                 l = std::max<long long>(Lw_min, (n + per_ch - 1) / per_ch);
             }
             l = std::min<long long>(std::max<long long>(l, 32), 1 << 30);
