@@ -258,7 +258,7 @@ def run_b200(args):
     sym = sym_dev[: 2 * nsym].view(-1, 2)[:, 0]
     checksum = int(torch.clamp(sym * 127, -128, 127).to(torch.int32).sum().item()) & 0xFFFFFFFF
 
-    # ---- end to end through the public host-buffer API
+    # ---- end to end through the public host-buffer API (xrd_demod_batch: pinned host input -> host symbols)
     step_e2e()
     torch.cuda.synchronize()
     shard.barrier()
@@ -267,8 +267,47 @@ def run_b200(args):
     for _ in range(ke):
         nsym_e = step_e2e()
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - te) * 1e3 / ke
+    e2e_seq_ms = (time.perf_counter() - te) * 1e3 / ke
     assert nsym_e == nsym
+
+    # The same calls double-buffered: two demodulator handles, two host threads, consecutive steps in flight
+    # together, so the PCIe copies of one step overlap the kernels of the other (and its kernels fill the SMs the
+    # other's certified re-run rounds leave idle).  Every step still copies its 1 GB in and its symbols out inside
+    # the timed region and starts from the freshly constructed loop state.
+    e2e_ms, in_flight = e2e_seq_ms, 1
+    if not args.no_overlap:
+        d2 = demod.Demodulator(mode="hrit", device_ordinal=local)
+        h_sym2 = torch.empty(2 * cap, dtype=torch.float32).pin_memory()
+        handles = [(d, h_sym), (d2, h_sym2)]
+        kp = max(4, 2 * ke)
+        counts = [[] for _ in handles]
+
+        def work(i):
+            dd, hs = handles[i]
+            cnt = np.zeros(1, np.int64)
+            for _ in range(kp // 2 + 1 if i == 0 and kp % 2 else kp // 2):
+                dd.reset()
+                rcode = demod.lib().xrd_demod_batch(dd._h, C.c_void_p(h_in.data_ptr()), n, 0, C.c_void_p(hs.data_ptr()),
+                                                    cap, cnt.ctypes.data_as(C.POINTER(C.c_int64)))
+                counts[i].append((rcode, int(cnt[0])))
+
+        def run_pair():
+            th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+            t0 = time.perf_counter()
+            [a.start() for a in th]
+            [a.join() for a in th]
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) * 1e3
+
+        run_pair()                      # warm-up (allocations of the second handle)
+        counts = [[] for _ in handles]
+        shard.barrier()
+        tot_ms = run_pair()
+        done = sum(len(c) for c in counts)
+        assert all(rc == 0 and ns == nsym for c in counts for rc, ns in c), counts
+        assert torch.equal(h_sym[: 2 * nsym], h_sym2[: 2 * nsym])
+        e2e_ms, in_flight = tot_ms / done, 2
+        d2.close()
 
     rec = shard.StreamRecord(rank=rank, n_streams=1, n_samples=n * args.steps, n_symbols=nsym * args.steps,
                              elapsed_ms=elapsed, checksum=checksum)
@@ -322,7 +361,10 @@ def run_b200(args):
                    "l2": "input (%.2f GB) and every intermediate exceed the 126 MB L2; no flush needed" % (8 * n / 1e9),
                    "parallelism": "1 stream per GPU, no data-path collective"},
         "e2e": {"value": agg_e["msps"], "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * nsym,
-                "ms_per_step": agg_e["elapsed_ms"]},
+                "ms_per_step": agg_e["elapsed_ms"], "steps_in_flight": in_flight,
+                "one_step_at_a_time": {"value": n / e2e_seq_ms / 1e3, "ms_per_step": e2e_seq_ms},
+                "note": "xrd_demod_batch on pinned host buffers; steps_in_flight = 2: consecutive steps double-buffered "
+                        "over two handles so copies overlap kernels; every step's H2D and D2H are inside the timed region"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -342,6 +384,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--samples", type=int, default=N_STREAM)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="e2e: one step at a time only (no double buffering)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
