@@ -133,7 +133,8 @@ typedef struct {
                                     0x20000 + (slots per thread << 8) + warps = window-Newton chain of that shape */
     int32_t loop_kernel;         /* AGC/Costas kernel: 0 default, 1 one thread per segment, 2 window-Newton warp chains,
                                     3..6 window-Newton CTA chains with (slots per thread, warps) = (1,4) (2,4) (1,2) (2,2) */
-    int32_t h2d_pieces;          /* host-input calls: copy/compute pieces (0 default = up to 2 of >= 16 M samples, 1 = one copy) */
+    int32_t h2d_pieces;          /* host-input calls: copy/compute pieces (low byte; 0 default = up to 2, 1 = one copy) and,
+                                    above it, the minimum piece in Ki samples (0 default = 16 M samples) */
     int32_t reserved;            /* tuning experiments: chains per SM, Costas | AGC << 8 (0 keeps defaults) */
 } xrd_tuning;
 int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t);

@@ -180,6 +180,19 @@ def test_chain_in_cfilefrontend_blocks(gpu, xrd, oracle):
     check_symbols(np.concatenate(parts), ref, "chain in 65535 blocks")
 
 
+@pytest.mark.parametrize("pieces", [2, 3, 5])
+def test_host_calls_in_pieces(gpu, xrd, oracle, pieces):
+    """host-input calls copy and run the sample-rate stages piece by piece (warm-ups reach back into earlier
+    pieces): same symbols as one copy, across two calls"""
+    _, x = make_signal("hrit", 1 << 21)
+    ref = oracle.Chain(oracle.config(True)).process(x)
+    d = xrd.Demodulator(mode="hrit")
+    d.set_tuning(h2d_pieces=pieces | (100 << 8))     # pieces of >= 100 Ki samples
+    cut = 1_200_003
+    got = np.concatenate([d.demod(x[:cut]), d.demod(x[cut:])])
+    check_symbols(got, ref, "%d pieces" % pieces)
+
+
 def test_chain_fifo_seam(gpu, xrd, oracle):
     """onSamplesAvailable -> FIFO -> processSamples -> SymbolManager::add"""
     _, x = make_signal("lrit", 600000)

@@ -1321,7 +1321,8 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
     d->mm.force64 = (t->mm_lanes & 0x10000) != 0;
     if (t->mm_warm) d->mm.W = t->mm_warm;
     if (t->h2d_pieces < 0) return XRD_E_ARG;
-    if (t->h2d_pieces) d->max_pieces = t->h2d_pieces;
+    if (t->h2d_pieces & 0xff) d->max_pieces = t->h2d_pieces & 0xff;
+    if (t->h2d_pieces >> 8) d->piece_min = (long long)(t->h2d_pieces >> 8) * 1024;
     return XRD_OK;
 }
 
