@@ -130,7 +130,9 @@ typedef struct {
     int64_t mm_seg, mm_warm;
     int32_t mm_lanes;            /* M&M chain kernel (tests/tuning): 0 default (mm_chain32_kernel, 1024 lanes); 128/256/512/1024 =
                                     mm_chain32_kernel with that many lanes (+0x10000: the generic 64-bit kernel);
-                                    0x20000 + (slots per thread << 8) + warps = window-Newton chain of that shape */
+                                    0x20000 + (slots per thread << 8) + warps = window-Newton chain of that shape;
+                                    + 0x40000: certified re-runs with the chain kernel instead of the relative walk
+                                    (mm_delta_kernel); + (1|2) << 20: 128|256 lanes for that walk */
     int32_t loop_kernel;         /* AGC/Costas kernel: 0 default, 1 one thread per segment, 2 window-Newton warp chains,
                                     3..6 window-Newton CTA chains with (slots per thread, warps) = (1,4) (2,4) (1,2) (2,2) */
     int32_t h2d_pieces;          /* host-input calls: copy/compute pieces (low byte; 0 default = up to 2, 1 = one copy) and,
@@ -147,6 +149,7 @@ typedef struct {
     uint64_t mm_windows, mm_iters;                       /* fixed-point windows / iterations */
     uint64_t agc_iters, costas_iters;                    /* window-Newton iterations (all warps) */
     float ms_fir_dec, ms_agc, ms_fir_rrc, ms_costas, ms_mm;  /* device time of the last call (CUDA events) */
+    uint64_t mm_bail;                                    /* relative (delta) re-runs that fell back to the chain kernel */
 } xrd_stats;
 int xrd_get_stats(xrd_demod *d, xrd_stats *s);
 

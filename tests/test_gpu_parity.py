@@ -159,6 +159,25 @@ def test_mm_chain_kernels_agree(gpu, xrd, oracle, mode, lanes):
     assert d.stats()["mm_redo"] > 0
 
 
+@pytest.mark.parametrize("warm", [60000, 20000, 1500])
+@pytest.mark.parametrize("lanes", [0, 1 << 20, 2 << 20, 0x40000])
+def test_mm_relative_reruns(gpu, xrd, oracle, lanes, warm):
+    """certified M&M re-runs as a walk relative to the trajectory in place (mm_delta_kernel: 128 and 256 lanes) and
+    with the chain kernel (0x40000) give the oracle's symbols; a warm-up too short to land near the true trajectory
+    makes the walk give up and fall back to the chain kernel"""
+    _, x = make_signal("hrit", 1 << 21)
+    ref = oracle.Chain(oracle.config(True)).process(x)
+    d = xrd.Demodulator(mode="hrit")
+    d.set_tuning(mm_lanes=lanes, mm_seg=100000, mm_warm=warm)
+    third = len(x) // 3 + 777
+    got = np.concatenate([d.demod(x[:third]), d.demod(x[third:2 * third]), d.demod(x[2 * third:])])
+    check_symbols(got, ref, "M&M re-runs %#x, warm-up %d" % (lanes, warm))
+    st = d.stats()
+    assert st["mm_redo"] > 0
+    if lanes & 0x40000:
+        assert st["mm_bail"] == 0
+
+
 # ------------------------------------------------------------------ the chain (processSamples)
 @pytest.mark.parametrize("mode,n", [("lrit", 1 << 20), ("hrit", 1 << 22)])
 def test_chain_one_shot(gpu, xrd, oracle, mode, n):

@@ -16,7 +16,7 @@ cap = d.symbol_capacity(n)
 sym = torch.empty(2 * cap, dtype=torch.float32, device="cuda")
 ref = None
 for spec in sys.argv[2:] or [""]:
-    kw = {k: int(v) for k, v in (kv.split("=") for kv in spec.split(",") if kv)}
+    kw = {k: int(v, 0) for k, v in (kv.split("=") for kv in spec.split(",") if kv)}
     d = demod.Demodulator(mode="hrit")
     if kw:
         d.set_tuning(**kw)
@@ -29,7 +29,7 @@ for spec in sys.argv[2:] or [""]:
         torch.cuda.synchronize(); dt = (time.perf_counter() - t) * 1e3
         s1 = d.stats()
         if best is None or dt < best[0]:
-            best = (dt, s1, {k: s1[k] - s0[k] for k in s1 if k.endswith(("rounds", "redo", "iters", "launches"))})
+            best = (dt, s1, {k: s1[k] - s0[k] for k in s1 if k.endswith(("rounds", "redo", "iters", "launches", "bail", "windows"))})
     digest = hashlib.sha1(sym[: 2 * ns].cpu().numpy().tobytes()).hexdigest()[:12]
     if ref is None:
         ref = digest

@@ -509,6 +509,11 @@ struct MmStage {
     int sm_count = 148;
     int nch = 1;
     DevBuf d_table, d_carried, d_entry, d_exit, d_redo, d_nredo, d_segout, d_offsets, d_stage, d_overflow, d_ckpt;
+    DevBuf d_traj;                  // per-symbol trajectory record (MmTraj), same indexing as d_stage
+    bool use_delta = true;          // certified re-runs walk relative to the trajectory in place (mm_delta_kernel)
+    int delta_nt = 256;             // lanes of mm_delta_kernel
+    bool traj_on = false;           // this call records the trajectory (more than one segment, 32-bit chain kernel)
+    uint64_t bails = 0;             // delta re-runs that gave up and fell back to the chain kernel
     int ck_spacing = 65536;         // samples between chain checkpoints
     int *h_nredo = nullptr;
     std::vector<long long> h_offsets;
@@ -536,12 +541,52 @@ struct MmStage {
         s_init.omega = omega;
         d_carried.ensure(sizeof(MmState) * nch);
         reset();
-        d_nredo.ensure(sizeof(int));
+        d_nredo.ensure(2 * sizeof(int));   // [0] segments flagged by the verify pass, [1] delta re-runs that gave up
         d_overflow.ensure(sizeof(int));
-        if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, 2 * sizeof(int)));
+        if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, 4 * sizeof(int)));
         int dev = 0;
         XRD_CUDA(cudaGetDevice(&dev));
         XRD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    MmTraj traj()
+    {
+        MmTraj tr{nullptr};
+        if (traj_on) tr.rec = d_traj.as<int4>();
+        return tr;
+    }
+    // the 32-bit chain kernel needs small per-symbol deviations (see its header comment) and 31-bit indices
+    bool fast32(int NT, long long n, long long Lseg, long long cap_seg) const
+    {
+        const double dev_max = (double)NT * prm.gain_omega + prm.gain_mu;
+        return !force64 && n < (1LL << 30) && Lseg < (1LL << 30) && W < (1LL << 30) && cap_seg < (1LL << 30) &&
+               32.0 * dev_max < 0.45 && 2.0 * prm.omega_lim + prm.gain_mu < 0.45 && prm.omega_mid < 1024.f;
+    }
+    // certified re-run of the flagged segments relative to the recorded trajectory; segments it gives up on stay flagged
+    void launch_delta(Counters &c, cudaStream_t st, dim3 grid, const float2 *in, long long n, long long Lseg, int nseg,
+                      long long cap_seg, long long in_stride, long long stage_stride)
+    {
+        const int ncp = (int)(Lseg / ck_spacing) + 2;
+        const double adv = (double)prm.omega_mid + (double)prm.omega_lim + (double)prm.gain_mu + 0.01;
+        if (delta_nt != 128 && delta_nt != 256) delta_nt = 256;
+        int NTd = delta_nt, RX = 0;
+        for (;; NTd >>= 1) {
+            // samples of five windows: the one being read and the four slides its request may lag behind
+            RX = next_pow2((long long)(5 * NTd * adv) + 96);
+            if (mm_delta_smem_bytes(NTd, RX) <= 190 * 1024 || NTd <= 128) break;
+        }
+        if (mm_delta_smem_bytes(NTd, RX) > 190 * 1024) return;   // symbols too long: the chain kernel takes all of it
+#define XRD_MM_DELTA(NTV)                                                                                               \
+    do {                                                                                                                \
+        const size_t smem = mm_delta_smem_bytes(NTV, RX);                                                               \
+        XRD_CUDA(cudaFuncSetAttribute(mm_delta_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        XRD_LAUNCH(c, mm_delta_kernel<NTV>, grid, NTV, smem, st, in, d_stage.as<float2>(), traj(), (int)n, (int)Lseg,    \
+                   nseg, (int)cap_seg, d_entry.as<MmState>(), d_exit.as<MmState>(), d_redo.as<unsigned char>(),         \
+                   d_segout.as<MmSegOut>(), d_table.as<float>(), prm, in_stride, stage_stride, d_ckpt.as<MmCk>(), ncp,  \
+                   d_nredo.as<int>() + 1, RX);                                                                          \
+    } while (0)
+        if (NTd == 128) XRD_MM_DELTA(128);
+        else XRD_MM_DELTA(256);
+#undef XRD_MM_DELTA
     }
     // launch the chain kernel with the widest window whose sample ring fits in shared memory
     void launch_chain(Counters &c, cudaStream_t st, dim3 grid, const float2 *in, long long n, long long Lseg, int nseg,
@@ -555,10 +600,7 @@ struct MmStage {
             R = next_pow2((long long)(2 * NT * adv) + 160);
             if (mm_chain32_smem_bytes(NT, R) <= 200 * 1024 || NT <= 128) break;
         }
-        // the 32-bit kernel needs small per-symbol deviations (see its header comment) and 31-bit indices
-        const double dev_max = (double)NT * prm.gain_omega + prm.gain_mu;
-        const bool fast = !force64 && n < (1LL << 30) && Lseg < (1LL << 30) && W < (1LL << 30) && cap_seg < (1LL << 30) &&
-                          32.0 * dev_max < 0.45 && 2.0 * prm.omega_lim + prm.gain_mu < 0.45 && prm.omega_mid < 1024.f;
+        const bool fast = fast32(NT, n, Lseg, cap_seg);
         if (fast && wn_k > 0) {
             // window-Newton chain: K slots per thread, WPC warps (xrd_mmwn.cuh)
             const int NTw = 32 * wn_wpc * wn_k;
@@ -595,7 +637,7 @@ struct MmStage {
         XRD_LAUNCH(c, mm_chain32_kernel<NTV>, grid, NTV, smem32, st, in, d_stage.as<float2>(), (int)n, (int)Lseg, (int)W, \
                    nseg, (int)cap_seg, d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(),             \
                    d_redo.as<unsigned char>(), d_segout.as<MmSegOut>(), d_table.as<float>(), prm, mode, in_stride,       \
-                   stage_stride, R, d_ckpt.as<MmCk>(), ncp, ck_spacing);                                                 \
+                   stage_stride, R, d_ckpt.as<MmCk>(), ncp, ck_spacing, traj());                                         \
     } while (0)
             if (NT >= 1024) XRD_MM_CHAIN32(1024);
             else if (NT == 512) XRD_MM_CHAIN32(512);
@@ -659,6 +701,12 @@ struct MmStage {
         d_stage.ensure(sizeof(float2) * (size_t)cap_seg * tot);
         const long long stage_stride = cap_seg * nseg;
         dim3 grid(nseg, nch);
+        // record the trajectory when there are hand-offs to certify and the kernel that records it will run
+        traj_on = use_delta && nseg > 1 && wn_k == 0 && fast32(nt ? nt : 1024, n, Ls, cap_seg);
+        if (traj_on) {
+            d_traj.ensure(sizeof(int4) * (size_t)cap_seg * tot);
+        }
+        XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, 2 * sizeof(int), st));
         launch_chain(c, st, grid, in, n, Ls, nseg, cap_seg, 0, in_stride, stage_stride);
         for (int round = 0; nseg > 1 && round < nseg; round++) {
             XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, sizeof(int), st));
@@ -670,6 +718,8 @@ struct MmStage {
             if (*h_nredo == 0) break;
             rounds++;
             redone += (uint64_t)*h_nredo;
+            // the delta kernel clears the flag of every segment it finishes; the chain kernel takes what is left
+            if (traj_on) launch_delta(c, st, grid, in, n, Ls, nseg, cap_seg, in_stride, stage_stride);
             launch_chain(c, st, grid, in, n, Ls, nseg, cap_seg, 1, in_stride, stage_stride);
         }
         XRD_CUDA(cudaMemsetAsync(d_overflow.p, 0, sizeof(int), st));
@@ -687,7 +737,9 @@ struct MmStage {
                                  cudaMemcpyDeviceToHost, st));
         XRD_CUDA(cudaMemcpyAsync(so.data(), d_segout.p, sizeof(MmSegOut) * tot, cudaMemcpyDeviceToHost, st));
         XRD_CUDA(cudaMemcpyAsync(h_nredo + 1, d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        XRD_CUDA(cudaMemcpyAsync(h_nredo + 2, d_nredo.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         XRD_CUDA(cudaStreamSynchronize(st));
+        bails += (uint64_t)h_nredo[2];
         int rc = XRD_OK;
         for (int ch = 0; ch < nch; ch++) {
             const long long cnt = h_offsets[(size_t)ch * (nseg + 1) + nseg];
@@ -1314,11 +1366,17 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
     if (t->mm_lanes & 0x20000) {   // window-Newton chain with (slots per thread << 8 | warps)
         d->mm.wn_k = (t->mm_lanes >> 8) & 0xff;
         d->mm.wn_wpc = t->mm_lanes & 0xff;
-    } else if (t->mm_lanes) {      // mm_chain32_kernel with that many lanes (+0x10000: the generic 64-bit kernel)
+    } else if (t->mm_lanes & 0xffff) {   // mm_chain32_kernel with that many lanes (+0x10000: the generic 64-bit kernel)
         d->mm.nt = t->mm_lanes & 0xffff;
         d->mm.wn_k = 0;
     }
     d->mm.force64 = (t->mm_lanes & 0x10000) != 0;
+    d->mm.use_delta = (t->mm_lanes & 0x40000) == 0;
+    switch ((t->mm_lanes >> 20) & 0xf) {
+    case 1: d->mm.delta_nt = 128; break;
+    case 2: d->mm.delta_nt = 256; break;
+    default: break;
+    }
     if (t->mm_warm) d->mm.W = t->mm_warm;
     if (t->h2d_pieces < 0) return XRD_E_ARG;
     if (t->h2d_pieces & 0xff) d->max_pieces = t->h2d_pieces & 0xff;
@@ -1339,6 +1397,7 @@ int xrd_get_stats(xrd_demod *d, xrd_stats *s)
     s->mm_redo = d->mm.redone;
     s->mm_windows = d->mm.windows;
     s->mm_iters = d->mm.iters;
+    s->mm_bail = d->mm.bails;
     s->agc_iters = d->agc.wn_iters();
     s->costas_iters = d->costas.wn_iters();
     s->ms_fir_dec = d->ms[0];

@@ -38,6 +38,11 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // NCO sine/cosine for |x| <= 2*pi (+slack): Cody-Waite by pi/2, Cephes polynomials.
@@ -627,6 +632,12 @@ struct MmCk {
     int pad;
 };
 
+// per-symbol record of the trajectory in place: the state BEFORE every symbol a segment emitted (same indexing as the
+// staging slots), in the fixed point of mm_chain32_kernel.  mm_delta_kernel re-runs a segment relative to it.
+struct MmTraj {
+    int4 *rec;      // x: interpolation base (sample index in the chunk), y: mu * 2^32, z: (omega - omega_mid) * 2^32
+};
+
 // mode 0: first pass (warm-up from a speculative state, or from `carried` when the warm-up reaches
 // the chunk start); mode 1: re-run of segments flagged in `redo` from entry[j].
 __global__ void __launch_bounds__(32)
@@ -1086,7 +1097,7 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
                   MmState *__restrict__ entry, MmState *__restrict__ exit_, const MmState *__restrict__ carried,
                   const unsigned char *__restrict__ redo, MmSegOut *__restrict__ segout, const float *__restrict__ table,
                   MmParams prm, int mode, long long in_ch_stride, long long stage_ch_stride, int R, MmCk *__restrict__ ckpt,
-                  int ncp, int C)
+                  int ncp, int C, MmTraj tr)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     float *s_tab = reinterpret_cast<float *>(s_raw);
@@ -1104,6 +1115,7 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
     const int j = blockIdx.x, ch = blockIdx.y;
     in += (size_t)ch * in_ch_stride;
     stage += (size_t)ch * stage_ch_stride + (size_t)j * cap_seg;
+    if (tr.rec) tr.rec += (size_t)ch * stage_ch_stride + (size_t)j * cap_seg;
     entry += (size_t)ch * nseg;
     exit_ += (size_t)ch * nseg;
     segout += (size_t)ch * nseg;
@@ -1306,8 +1318,11 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
         }
         if (r >= lo && r < hi) {
             const int pos = count + (r - lo);
-            if (pos < cap_seg) stage[pos] = p0;
-            else overflow = 1;
+            if (pos < cap_seg) {
+                stage[pos] = p0;
+                // accepted lanes did not change: (ii, fr, wr) is the exact state before this symbol
+                if (tr.rec) tr.rec[pos] = make_int4(ii, (int)fr, wr, 0);
+            } else overflow = 1;
         }
         if (ck && have_entry) {
             // checkpoint: first symbol at or after sample next_ck, if its state is exact already (r_ck <= hi)
@@ -1411,6 +1426,330 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
         }
         segout[j] = so;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Certified re-run of a segment RELATIVE to the trajectory already in place (mm_delta_kernel).
+//
+// A segment whose hand-off failed ran from a warm-up state B that is a few grid units away from the
+// true state A.  Two such trajectories see the same interpolator rows (ii, k) and therefore the same
+// timing errors for hundreds of symbols at a time, so A's states are B's recorded states (MmTraj)
+// shifted by a constant: T_A[s] = T_B[s] + dT + (s - m) * dW, w_A[s] = w_B[s] + dW.  One CTA walks
+// the segment in windows of NT symbols: lane r believes that shifted state, reuses B's interpolant
+// when (ii, k) agree (fresh interpolation otherwise), applies the LITERAL loop update, and the window
+// is accepted up to the first lane whose believed state is not bit for bit the update result of its
+// predecessor -- the same literal acceptance from an exact base as the window-Newton kernels, so the
+// result is the sequential trajectory exactly; the hypothesis only decides how far one iteration gets.
+// At a break the offsets are re-fitted from the measured jumps of the next three lanes (one
+// interpolant enters three consecutive timing errors).  The walk stops when A is bitwise B (state and
+// the two interpolants of the history): the rest of the segment is in place already.  Staging slots and
+// trajectory records are patched in place.  A walk that advances too slowly (B was not close: cold
+// start, cycle slip, symbol indices out of step) gives up and leaves redo[j] set; the host then runs
+// mm_chain32_kernel (mode 1) on what is left flagged.
+// ---------------------------------------------------------------------------------------
+constexpr long long MM_NOSTATE = (long long)0x8000000000000000ULL;
+constexpr int MM_DELTA_RING = 8;   // ring capacity of mm_delta_kernel in windows (>= 6: three groups in flight)
+// RX: capacity of the sample ring (power of two, >= 5 windows of samples: see the in-flight accounting in the kernel)
+__host__ __device__ inline size_t mm_delta_smem_bytes(int NT, int RX)
+{
+    return (size_t)MM_DELTA_RING * NT * (sizeof(int4) + sizeof(float2)) + sizeof(float2) * (size_t)RX;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+mm_delta_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, MmTraj tr, int n, int L, int nseg, int cap_seg,
+                const MmState *__restrict__ entry, MmState *__restrict__ exit_, unsigned char *__restrict__ redo,
+                MmSegOut *__restrict__ segout, const float *__restrict__ table, MmParams prm, long long in_ch_stride,
+                long long stage_ch_stride, MmCk *__restrict__ ckpt, int ncp, int *__restrict__ n_bail, int RX)
+{
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    constexpr int R = MM_DELTA_RING * NT, RM = R - 1;
+    int4 *s_tr = reinterpret_cast<int4 *>(s_dyn);        // [R] ring of trajectory records, symbol s in slot s & RM
+    float2 *s_pb = reinterpret_cast<float2 *>(s_tr + R);  // [R] ring of the interpolants in place
+    float2 *s_x = s_pb + R;                               // [RX] ring of input samples, sample i in slot i & RXM
+    const int RXM = RX - 1;
+    __shared__ float s_tab[MM_TAB_PAD];
+    __shared__ float2 s_p[2][NT];            // interpolants, double buffered
+    __shared__ unsigned char s_same[2][NT];  // interpolant bitwise equal to the one in place
+    __shared__ long long s_nT[NT], s_jT[NT];   // update result / jump against the belief
+    __shared__ int s_nW[NT], s_jW[NT];
+    __shared__ unsigned s_min[2][2];
+    constexpr int M = NT - 1;
+    constexpr int BIG = 1 << 30;
+    const int t = threadIdx.x;
+    const int j = blockIdx.x, ch = blockIdx.y;
+    redo += (size_t)ch * nseg;
+    if (!redo[j]) return;
+    in += (size_t)ch * in_ch_stride;
+    {
+        const size_t o = (size_t)ch * stage_ch_stride + (size_t)j * cap_seg;
+        stage += o;
+        tr.rec += o;
+    }
+    entry += (size_t)ch * nseg;
+    exit_ += (size_t)ch * nseg;
+    segout += (size_t)ch * nseg;
+    for (int i = t; i < 129 * 8; i += NT) {
+        const int k = i >> 3, tp = i & 7;
+        s_tab[tp * 129 + k] = table[i];
+    }
+    if (t < 4) (&s_min[0][0])[t] = NT;
+    __shared__ int s_fresh;   // interpolations that could not be taken from the trajectory in place (diagnostic)
+    if (t == 0) s_fresh = 0;
+    const int seg1 = (j == nseg - 1) ? BIG : (j + 1) * L;
+    const int last_ok = n - MM_NTAPS;
+    const int lo_min = -MM_TAIL;
+    const float omid = prm.omega_mid;
+    const int countB = min(segout[j].n_sym, cap_seg);
+    const MmState st = entry[j];
+    // exact base (uniform): state before symbol m, interpolants of symbols m-1 and m-2
+    long long Tb = ((long long)(int)st.ii << 32) + (unsigned)(st.mu * MM_FIX);
+    int wb = (int)((st.omega - omid) * MM_FIX);
+    float2 P1 = st.p0, P2 = st.p1;
+    bool same1 = false, same2 = false;
+    int m = 0, tb = 0, par = 0, iters = 0, overflow = 0;
+    // the records and interpolants in place are streamed into the rings R - NT symbols ahead of the window: one
+    // cp.async group per iteration, and a window only reads groups older than the latest
+    // and so are the input samples behind the base (for the interpolations that cannot be reused).  xf[0] = samples
+    // requested so far, xf[4] = samples every thread may read in this iteration (requested five slides ago: three
+    // groups stay in flight, and a thread's wait is published by the barriers of the following iteration)
+    int fill = 0;
+    int xf[5];
+    xf[0] = ((int)st.ii < lo_min ? lo_min : (int)st.ii) & ~31;
+    auto refill = [&](int target, int ii_base) {
+        const int top = min(target, countB);
+        for (int s = fill + t; s < top; s += NT) {
+            cp_async16(&s_tr[s & RM], tr.rec + s);
+            cp_async8(&s_pb[s & RM], stage + s);
+        }
+        if (target > fill) fill = target;
+        const int xt = ((ii_base < lo_min ? lo_min : ii_base) & ~31) + RX;
+        for (int i = xf[0] + t; i < xt; i += NT)
+            if (i >= lo_min && i < n) cp_async8(&s_x[i & RXM], in + i);
+        if (xt > xf[0]) xf[0] = xt;
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    refill(R, (int)st.ii);
+    xf[1] = xf[2] = xf[3] = xf[4] = xf[0];
+    cp_async_wait_all();
+    __syncthreads();
+    // offsets of the belief: lanes r >= 2 believe (TB + dT + r * dW, wB + dW), lane 1 (TB + d1T, wB + d1W)
+    long long dT = 0, d1T = 0;
+    int dW = 0, d1W = 0;
+    if (countB > 0) {
+        const int4 b0 = s_tr[0];
+        dT = Tb - (((long long)b0.x << 32) + (unsigned)b0.y);
+        dW = wb - b0.z;
+        d1T = dT + dW;
+        d1W = dW;
+    }
+    bool merged = false, bail = false, done = false;
+
+    for (;;) {
+        if (iters > 64 + (m >> 3)) { bail = true; break; }
+        iters++;
+        const int r = (t - tb) & M;
+        float2 *sp = s_p[par];
+        unsigned char *ssame = s_same[par];
+        // ---- 1. believed state and its interpolant
+        long long TB = MM_NOSTATE;   // the state in place at this lane's symbol
+        int wB = 0, iiB = 0, kB = -1;
+        float2 p0B = make_float2(0.f, 0.f);
+        if (m + r < countB) {
+            const int4 b = s_tr[(m + r) & RM];
+            p0B = s_pb[(m + r) & RM];
+            iiB = b.x;
+            wB = b.z;
+            TB = ((long long)b.x << 32) + (unsigned)b.y;
+            kB = (int)rintf(((float)(unsigned)b.y * MM_UNFIX) * (float)MM_NSTEPS);
+        }
+        long long T;
+        int w;
+        bool valid = true;
+        if (r == 0) { T = Tb; w = wb; }
+        else if (TB != MM_NOSTATE) {
+            if (r == 1) { T = TB + d1T; w = wB + d1W; }
+            else { T = TB + dT + (long long)r * dW; w = wB + dW; }
+        } else { T = 0; w = 0; valid = false; }
+        const int ii = (int)(T >> 32);
+        const unsigned fr = (unsigned)T;
+        const float mu = (float)fr * MM_UNFIX;
+        const float om = fmaf((float)w, MM_UNFIX, omid);   // exact
+        const int k = (int)rintf(mu * (float)MM_NSTEPS);
+        const bool stopc = valid && ((ii > last_ok) || (ii >= seg1));
+        const bool match = valid && TB != MM_NOSTATE && ii == iiB && k == kB;
+        float2 p0;
+        if (match) p0 = p0B;
+        else if (valid && !stopc && ii >= lo_min && ii >= xf[0] - RX && ii + MM_NTAPS <= xf[4]) {
+            float ar[4], ai[4];
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                const float t0 = s_tab[(7 - l) * 129 + k];
+                const float t1 = s_tab[(3 - l) * 129 + k];
+                const float2 a = s_x[(ii + l) & RXM], bb = s_x[(ii + l + 4) & RXM];
+                ar[l] = fmaf(t1, bb.x, t0 * a.x);
+                ai[l] = fmaf(t1, bb.y, t0 * a.y);
+            }
+            p0 = make_float2((ar[0] + ar[1]) + (ar[2] + ar[3]), (ai[0] + ai[1]) + (ai[2] + ai[3]));
+            atomicAdd(&s_fresh, 1);
+        } else {
+            p0 = make_float2(0.f, 0.f);
+            if (!stopc) valid = false;
+        }
+        sp[t] = p0;
+        ssame[t] = (TB != MM_NOSTATE) && __float_as_uint(p0.x) == __float_as_uint(p0B.x) &&
+                   __float_as_uint(p0.y) == __float_as_uint(p0B.y);
+        __syncthreads();   // S1
+        // merged with the trajectory in place: same state before symbol m, same history
+        if (m >= 2 && same1 && same2 && m < countB) {
+            const int4 b = s_tr[m & RM];
+            if ((((long long)b.x << 32) + (unsigned)b.y) == Tb && b.z == wb) { merged = true; break; }
+        }
+        // ---- 2. literal loop update
+        float2 p1 = sp[(t - 1) & M], p2 = sp[(t - 2) & M];
+        if (r == 0) { p1 = P1; p2 = P2; }
+        if (r == 1) { p2 = P1; }
+        float mu2 = mu, om2 = om;
+        long long adv = 0;
+        mm_update(prm, p0, p1, p2, mu2, om2, adv);
+        const long long nT = ((long long)(ii + (int)adv) << 32) + (unsigned)(mu2 * MM_FIX);
+        const int nw = (int)((om2 - omid) * MM_FIX);
+        s_nT[t] = valid ? nT : MM_NOSTATE;
+        s_nW[t] = nw;
+        __syncthreads();   // S2
+        // ---- 3. literal acceptance: a lane is good if it could evaluate and its belief IS its predecessor's result
+        bool ok = valid;
+        {
+            long long jT = 0;
+            int jW = 0;
+            if (r > 0) {
+                const int tp = (t - 1) & M;
+                const long long pT = s_nT[tp];
+                if (valid && pT != MM_NOSTATE) {
+                    jT = pT - T;
+                    jW = s_nW[tp] - w;
+                    ok = (jT == 0) && (jW == 0);
+                } else {
+                    jT = MM_NOSTATE;
+                    ok = false;
+                }
+            }
+            s_jT[t] = jT;
+            s_jW[t] = jW;
+        }
+        const unsigned m0 = __reduce_min_sync(0xffffffffu, ok ? (unsigned)NT : (unsigned)r);
+        const unsigned m1 = __reduce_min_sync(0xffffffffu, stopc ? (unsigned)r : (unsigned)NT);
+        if ((t & 31) == 0) {
+            if (m0 < NT) atomicMin(&s_min[par][0], m0);
+            if (m1 < NT) atomicMin(&s_min[par][1], m1);
+        }
+        __syncthreads();   // S3
+        const int fb = (int)s_min[par][0];        // first lane that is not exact (>= 1: the base always is)
+        const int r_stop = (int)s_min[par][1];
+        if (fb == 0) { bail = true; break; }      // the base could not be evaluated (cannot happen for a state in range)
+        const bool stop = r_stop < fb;            // an exact lane is past the segment
+        const int hi = stop ? r_stop : fb;
+        if (r < hi) {
+            const int pos = m + r;
+            if (pos < cap_seg) {
+                if (!match) stage[pos] = p0;
+                if (TB == MM_NOSTATE || T != TB || w != wB) tr.rec[pos] = make_int4(ii, (int)fr, w, 0);
+            } else overflow = 1;
+        }
+        if (stop) {
+            if (r == r_stop) {
+                float2 q1 = sp[(t - 1) & M], q2 = sp[(t - 2) & M];
+                if (r == 0) { q1 = P1; q2 = P2; }
+                if (r == 1) { q2 = P1; }
+                MmState s;
+                s.ii = ii;
+                s.mu = mu;
+                s.omega = om;
+                s.p0 = q1;
+                s.p1 = q2;
+                exit_[j] = s;
+            }
+            m += hi;
+            done = true;
+            break;
+        }
+        // ---- 4. slide by fb: lane fb - 1's result is the new exact base
+        const int tl = (tb + fb - 1) & M;
+        const long long nTb = s_nT[tl];
+        const int nwb = s_nW[tl];
+        if (fb >= 2) {
+            const int t2 = (tb + fb - 2) & M;
+            P2 = sp[t2];
+            P1 = sp[tl];
+            same2 = ssame[t2] != 0;
+            same1 = ssame[tl] != 0;
+        } else {
+            P2 = P1;
+            P1 = sp[tb];
+            same2 = same1;
+            same1 = ssame[tb] != 0;
+        }
+        // re-fit the offsets from the jumps measured at lanes fb, fb + 1, fb + 2
+        {
+            long long a0 = 0, a1 = 0, a2 = 0;
+            int b0 = 0, b1 = 0, b2 = 0;
+            if (fb < NT) {
+                const int tf = (tb + fb) & M;
+                if (s_jT[tf] != MM_NOSTATE) { a0 = s_jT[tf]; b0 = s_jW[tf]; }
+                if (fb + 1 < NT) {
+                    const int tf1 = (tf + 1) & M;
+                    if (s_jT[tf1] != MM_NOSTATE) { a1 = s_jT[tf1]; b1 = s_jW[tf1]; }
+                }
+                if (fb + 2 < NT) {
+                    const int tf2 = (tf + 2) & M;
+                    if (s_jT[tf2] != MM_NOSTATE) { a2 = s_jT[tf2]; b2 = s_jW[tf2]; }
+                }
+            }
+            // lane fb + 1 had believed TB + dT + (fb + 1) * dW (fb >= 1, so it was not lane 1)
+            d1T = dT + (long long)(fb + 1) * dW + a0 + a1 + b0;
+            d1W = dW + b0 + b1;
+            dT = dT + (long long)fb * dW + a0 + a1 + a2 - ((long long)b1 + 2LL * (long long)b2);
+            dW = dW + b0 + b1 + b2;
+        }
+        tb = (tb + fb) & M;
+        m += fb;
+        Tb = nTb;
+        wb = nwb;
+        if (t < 2) s_min[par ^ 1][t] = NT;
+        par ^= 1;
+        // slots of symbols below the new base are free: stream in up to m + R.  Every thread then waits for all of its
+        // groups but the three newest (DRAM latency spans several iterations); the barriers of the next iteration
+        // publish them, so the window after that reads nothing above (base four slides ago) + R >= its own base + 2 NT
+        // (a slide is at most NT; R = 8 NT).
+        xf[4] = xf[3]; xf[3] = xf[2]; xf[2] = xf[1]; xf[1] = xf[0];
+        refill(m + R, (int)(Tb >> 32));
+        asm volatile("cp.async.wait_group 3;\n" ::: "memory");
+    }
+    cp_async_wait_all();
+    overflow = __syncthreads_or(overflow);
+    if (bail) {
+        if (t == 0) {
+            atomicAdd(n_bail, 1);
+            segout[j].iters += iters;
+        }
+        return;   // redo[j] stays set: the chain kernel re-runs this segment from entry[j]
+    }
+    // checkpoints recorded on the old trajectory inside the patched part no longer describe what is in place
+    if (ckpt) {
+        MmCk *ck = ckpt + ((size_t)ch * nseg + j) * ncp;
+        for (int i = t; i < ncp; i += NT)
+            if (done || ck[i].count < m) ck[i].count = -1;
+    }
+    if (t == 0) {
+        MmSegOut so = segout[j];
+        if (done) so.n_sym = m;
+        so.overflow |= overflow;
+        so.iters += iters;
+        so.windows += s_fresh;
+        segout[j] = so;
+        redo[j] = 0;
+    }
+    (void)merged;
 }
 
 // hand-off check for M&M: redo[j] = entry[j] != exit[j-1] (then entry[j] := exit[j-1])

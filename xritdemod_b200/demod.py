@@ -71,7 +71,7 @@ class Stats(C.Structure):
         ("mm_rounds", C.c_uint64), ("agc_redo", C.c_uint64), ("costas_redo", C.c_uint64), ("mm_redo", C.c_uint64),
         ("mm_windows", C.c_uint64), ("mm_iters", C.c_uint64), ("agc_iters", C.c_uint64),
         ("costas_iters", C.c_uint64), ("ms_fir_dec", C.c_float), ("ms_agc", C.c_float),
-        ("ms_fir_rrc", C.c_float), ("ms_costas", C.c_float), ("ms_mm", C.c_float),
+        ("ms_fir_rrc", C.c_float), ("ms_costas", C.c_float), ("ms_mm", C.c_float), ("mm_bail", C.c_uint64),
     ]
 
     def as_dict(self):
