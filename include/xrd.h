@@ -132,7 +132,7 @@ typedef struct {
                                     mm_chain32_kernel with that many lanes (+0x10000: the generic 64-bit kernel);
                                     0x20000 + (slots per thread << 8) + warps = window-Newton chain of that shape;
                                     + 0x40000: certified re-runs with the chain kernel instead of the relative walk
-                                    (mm_delta_kernel); + (1|2) << 20: 128|256 lanes for that walk */
+                                    (mm_delta_kernel); + (1|2|3) << 20: 128|256|512 lanes for that walk (default 512) */
     int32_t loop_kernel;         /* AGC/Costas kernel: 0 default, 1 one thread per segment, 2 window-Newton warp chains,
                                     3..6 window-Newton CTA chains with (slots per thread, warps) = (1,4) (2,4) (1,2) (2,2) */
     int32_t h2d_pieces;          /* host-input calls: copy/compute pieces (low byte; 0 default = up to 2, 1 = one copy) and,

@@ -162,7 +162,7 @@ def test_mm_chain_kernels_agree(gpu, xrd, oracle, mode, lanes):
 @pytest.mark.parametrize("warm", [60000, 20000, 1500])
 @pytest.mark.parametrize("lanes", [0, 1 << 20, 2 << 20, 0x40000])
 def test_mm_relative_reruns(gpu, xrd, oracle, lanes, warm):
-    """certified M&M re-runs as a walk relative to the trajectory in place (mm_delta_kernel: 128 and 256 lanes) and
+    """certified M&M re-runs as a walk relative to the trajectory in place (mm_delta_kernel: 512, 128 and 256 lanes) and
     with the chain kernel (0x40000) give the oracle's symbols; a warm-up too short to land near the true trajectory
     makes the walk give up and fall back to the chain kernel"""
     _, x = make_signal("hrit", 1 << 21)

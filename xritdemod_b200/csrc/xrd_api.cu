@@ -500,7 +500,11 @@ static int next_pow2(long long v)
 
 struct MmStage {
     MmParams prm;
-    long long L = 0, W = 800000;    // L == 0: one segment per SM (set per call); W: speculative warm-up (samples)
+    long long L = 0;                // 0: one segment per SM (set per call)
+    long long W_user = 0;           // speculative warm-up in samples; 0: 80 k when re-runs can walk relative to the recorded
+                                    // trajectory (which only needs the warm-up to land within a few grid units of the
+                                    // truth), 800 k when they are full chain re-runs (which need a bitwise merge)
+    long long W = 800000;           // the warm-up of the current call
     long long Lmin = 262144;
     int nt = 0;                     // lanes per chain of mm_chain32_kernel (0 = auto)
     int wn_k = 0, wn_wpc = 16;      // window-Newton chain kernel (xrd_mmwn.cuh): slots per thread, warps; 0 = mm_chain32_kernel,
@@ -511,7 +515,7 @@ struct MmStage {
     DevBuf d_table, d_carried, d_entry, d_exit, d_redo, d_nredo, d_segout, d_offsets, d_stage, d_overflow, d_ckpt;
     DevBuf d_traj;                  // per-symbol trajectory record (MmTraj), same indexing as d_stage
     bool use_delta = true;          // certified re-runs walk relative to the trajectory in place (mm_delta_kernel)
-    int delta_nt = 256;             // lanes of mm_delta_kernel
+    int delta_nt = 512;             // lanes of mm_delta_kernel (halved until its rings fit in shared memory)
     bool traj_on = false;           // this call records the trajectory (more than one segment, 32-bit chain kernel)
     uint64_t bails = 0;             // delta re-runs that gave up and fell back to the chain kernel
     int ck_spacing = 65536;         // samples between chain checkpoints
@@ -567,11 +571,12 @@ struct MmStage {
     {
         const int ncp = (int)(Lseg / ck_spacing) + 2;
         const double adv = (double)prm.omega_mid + (double)prm.omega_lim + (double)prm.gain_mu + 0.01;
-        if (delta_nt != 128 && delta_nt != 256) delta_nt = 256;
+        if (delta_nt != 128 && delta_nt != 256 && delta_nt != 512) delta_nt = 512;
         int NTd = delta_nt, RX = 0;
         for (;; NTd >>= 1) {
-            // samples of five windows: the one being read and the four slides its request may lag behind
-            RX = next_pow2((long long)(5 * NTd * adv) + 96);
+            // samples of five windows (the one being read and the four slides its request may lag behind) plus the
+            // block granularity of the refill
+            RX = next_pow2((long long)(5 * NTd * adv) + NTd + 96);
             if (mm_delta_smem_bytes(NTd, RX) <= 190 * 1024 || NTd <= 128) break;
         }
         if (mm_delta_smem_bytes(NTd, RX) > 190 * 1024) return;   // symbols too long: the chain kernel takes all of it
@@ -585,7 +590,8 @@ struct MmStage {
                    d_nredo.as<int>() + 1, RX);                                                                          \
     } while (0)
         if (NTd == 128) XRD_MM_DELTA(128);
-        else XRD_MM_DELTA(256);
+        else if (NTd == 256) XRD_MM_DELTA(256);
+        else XRD_MM_DELTA(512);
 #undef XRD_MM_DELTA
     }
     // launch the chain kernel with the widest window whose sample ring fits in shared memory
@@ -702,7 +708,9 @@ struct MmStage {
         const long long stage_stride = cap_seg * nseg;
         dim3 grid(nseg, nch);
         // record the trajectory when there are hand-offs to certify and the kernel that records it will run
+        W = W_user > 0 ? W_user : 80000;
         traj_on = use_delta && nseg > 1 && wn_k == 0 && fast32(nt ? nt : 1024, n, Ls, cap_seg);
+        if (!traj_on && W_user <= 0) W = 800000;
         if (traj_on) {
             d_traj.ensure(sizeof(int4) * (size_t)cap_seg * tot);
         }
@@ -1375,9 +1383,10 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
     switch ((t->mm_lanes >> 20) & 0xf) {
     case 1: d->mm.delta_nt = 128; break;
     case 2: d->mm.delta_nt = 256; break;
+    case 3: d->mm.delta_nt = 512; break;
     default: break;
     }
-    if (t->mm_warm) d->mm.W = t->mm_warm;
+    if (t->mm_warm) d->mm.W_user = t->mm_warm;
     if (t->h2d_pieces < 0) return XRD_E_ARG;
     if (t->h2d_pieces & 0xff) d->max_pieces = t->h2d_pieces & 0xff;
     if (t->h2d_pieces >> 8) d->piece_min = (long long)(t->h2d_pieces >> 8) * 1024;
@@ -1625,7 +1634,7 @@ int xrd_stage_set_tuning(xrd_stage *s, int64_t seg, int64_t warm)
         break;
     case xrd_stage::MM:
         if (seg) s->mm.L = std::max<long long>(seg, 64);
-        if (warm) s->mm.W = warm;
+        if (warm) s->mm.W_user = warm;
         break;
     default:
         break;

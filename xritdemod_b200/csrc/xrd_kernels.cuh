@@ -635,7 +635,8 @@ struct MmCk {
 // per-symbol record of the trajectory in place: the state BEFORE every symbol a segment emitted (same indexing as the
 // staging slots), in the fixed point of mm_chain32_kernel.  mm_delta_kernel re-runs a segment relative to it.
 struct MmTraj {
-    int4 *rec;      // x: interpolation base (sample index in the chunk), y: mu * 2^32, z: (omega - omega_mid) * 2^32
+    int4 *rec;      // x: interpolation base (sample index in the chunk), y: mu * 2^32, z: (omega - omega_mid) * 2^32,
+                    // w: interpolator row rint(mu * 128)
 };
 
 // mode 0: first pass (warm-up from a speculative state, or from `carried` when the warm-up reaches
@@ -1321,7 +1322,7 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
             if (pos < cap_seg) {
                 stage[pos] = p0;
                 // accepted lanes did not change: (ii, fr, wr) is the exact state before this symbol
-                if (tr.rec) tr.rec[pos] = make_int4(ii, (int)fr, wr, 0);
+                if (tr.rec) tr.rec[pos] = make_int4(ii, (int)fr, wr, k);
             } else overflow = 1;
         }
         if (ck && have_entry) {
@@ -1434,18 +1435,22 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
 // A segment whose hand-off failed ran from a warm-up state B that is a few grid units away from the
 // true state A.  Two such trajectories see the same interpolator rows (ii, k) and therefore the same
 // timing errors for hundreds of symbols at a time, so A's states are B's recorded states (MmTraj)
-// shifted by a constant: T_A[s] = T_B[s] + dT + (s - m) * dW, w_A[s] = w_B[s] + dW.  One CTA walks
-// the segment in windows of NT symbols: lane r believes that shifted state, reuses B's interpolant
-// when (ii, k) agree (fresh interpolation otherwise), applies the LITERAL loop update, and the window
-// is accepted up to the first lane whose believed state is not bit for bit the update result of its
-// predecessor -- the same literal acceptance from an exact base as the window-Newton kernels, so the
-// result is the sequential trajectory exactly; the hypothesis only decides how far one iteration gets.
-// At a break the offsets are re-fitted from the measured jumps of the next three lanes (one
-// interpolant enters three consecutive timing errors).  The walk stops when A is bitwise B (state and
-// the two interpolants of the history): the rest of the segment is in place already.  Staging slots and
+// shifted by an offset that drifts linearly: T_A[s] = T_B[s] + dT + (s - m) * dW, w_A[s] = w_B[s] + dW.
+// One CTA walks the segment in windows of NT symbols: lane r believes that shifted state for symbol
+// m + r, reuses B's interpolant when (ii, k) agree (fresh interpolation from the sample ring
+// otherwise), applies the LITERAL loop update and compares the result, bit for bit, with what lane
+// r + 1 believes.  The window is accepted up to the first lane whose belief is not its predecessor's
+// result -- literal acceptance from an exact base, as in the window-Newton kernels, so the result is
+// the sequential trajectory exactly; the hypothesis only decides how far one iteration gets.  At a
+// break the offsets are re-fitted from the jumps measured at the next three lanes (one interpolant
+// enters three consecutive timing errors).  The walk stops when A is bitwise B (state and the two
+// interpolants of the history): the rest of the segment is in place already.  Staging slots and
 // trajectory records are patched in place.  A walk that advances too slowly (B was not close: cold
 // start, cycle slip, symbol indices out of step) gives up and leaves redo[j] set; the host then runs
 // mm_chain32_kernel (mode 1) on what is left flagged.
+//
+// Records, interpolants in place and input samples are streamed into shared-memory rings with
+// cp.async, three groups in flight (DRAM latency spans several iterations).
 // ---------------------------------------------------------------------------------------
 constexpr long long MM_NOSTATE = (long long)0x8000000000000000ULL;
 constexpr int MM_DELTA_RING = 8;   // ring capacity of mm_delta_kernel in windows (>= 6: three groups in flight)
@@ -1469,12 +1474,12 @@ mm_delta_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, MmTra
     float2 *s_x = s_pb + R;                               // [RX] ring of input samples, sample i in slot i & RXM
     const int RXM = RX - 1;
     __shared__ float s_tab[MM_TAB_PAD];
-    __shared__ float2 s_p[2][NT];            // interpolants, double buffered
-    __shared__ unsigned char s_same[2][NT];  // interpolant bitwise equal to the one in place
-    __shared__ long long s_nT[NT], s_jT[NT];   // update result / jump against the belief
+    __shared__ float2 s_p[2][NT];              // interpolants, double buffered
+    __shared__ long long s_nT[NT], s_jT[NT];   // update result of lane r / its jump against the belief of lane r + 1
     __shared__ int s_nW[NT], s_jW[NT];
+    __shared__ unsigned char s_same[NT];       // interpolant bitwise equal to the one in place
     __shared__ unsigned s_min[2][2];
-    constexpr int M = NT - 1;
+    __shared__ int s_fresh;                    // interpolations that could not be taken from the trajectory (diagnostic)
     constexpr int BIG = 1 << 30;
     const int t = threadIdx.x;
     const int j = blockIdx.x, ch = blockIdx.y;
@@ -1494,7 +1499,6 @@ mm_delta_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, MmTra
         s_tab[tp * 129 + k] = table[i];
     }
     if (t < 4) (&s_min[0][0])[t] = NT;
-    __shared__ int s_fresh;   // interpolations that could not be taken from the trajectory in place (diagnostic)
     if (t == 0) s_fresh = 0;
     const int seg1 = (j == nseg - 1) ? BIG : (j + 1) * L;
     const int last_ok = n - MM_NTAPS;
@@ -1507,33 +1511,40 @@ mm_delta_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, MmTra
     int wb = (int)((st.omega - omid) * MM_FIX);
     float2 P1 = st.p0, P2 = st.p1;
     bool same1 = false, same2 = false;
-    int m = 0, tb = 0, par = 0, iters = 0, overflow = 0;
-    // the records and interpolants in place are streamed into the rings R - NT symbols ahead of the window: one
-    // cp.async group per iteration, and a window only reads groups older than the latest
-    // and so are the input samples behind the base (for the interpolations that cannot be reused).  xf[0] = samples
-    // requested so far, xf[4] = samples every thread may read in this iteration (requested five slides ago: three
-    // groups stay in flight, and a thread's wait is published by the barriers of the following iteration)
+    int m = 0, par = 0, iters = 0, overflow = 0;
+    // Rings.  xf[0] = samples requested so far, xf[4] = samples every thread may read in this iteration (requested
+    // five slides ago: three groups stay in flight, and a thread's wait is published by the barriers of the iteration
+    // after it).  Records are requested R symbols ahead of the base, which covers the same lag (R = 8 NT).
     int fill = 0;
     int xf[5];
     xf[0] = ((int)st.ii < lo_min ? lo_min : (int)st.ii) & ~31;
-    auto refill = [&](int target, int ii_base) {
-        const int top = min(target, countB);
-        for (int s = fill + t; s < top; s += NT) {
-            cp_async16(&s_tr[s & RM], tr.rec + s);
-            cp_async8(&s_pb[s & RM], stage + s);
+    // one block of NT records (a slide frees at most NT slots) and whole blocks of NT samples per call
+    auto refill = [&](int base_sym, int ii_base) {
+        if (fill + NT <= base_sym + R) {
+            const int s = fill + t;
+            if (s < countB) {
+                cp_async16(&s_tr[s & RM], tr.rec + s);
+                cp_async8(&s_pb[s & RM], stage + s);
+            }
+            fill += NT;
         }
-        if (target > fill) fill = target;
-        const int xt = ((ii_base < lo_min ? lo_min : ii_base) & ~31) + RX;
-        for (int i = xf[0] + t; i < xt; i += NT)
+        const int xt = (ii_base & ~31) + RX;
+        while (xf[0] + NT <= xt) {
+            const int i = xf[0] + t;
             if (i >= lo_min && i < n) cp_async8(&s_x[i & RXM], in + i);
-        if (xt > xf[0]) xf[0] = xt;
+            xf[0] += NT;
+        }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    refill(R, (int)st.ii);
+    {
+        const int x0 = xf[0];
+        for (int q = 0; q < MM_DELTA_RING; q++) refill(0, x0);   // one block of records per call until fill == R
+    }
     xf[1] = xf[2] = xf[3] = xf[4] = xf[0];
     cp_async_wait_all();
     __syncthreads();
-    // offsets of the belief: lanes r >= 2 believe (TB + dT + r * dW, wB + dW), lane 1 (TB + d1T, wB + d1W)
+    // offsets of the belief: lane r >= 2 believes (TB + dT + r * dW, wB + dW), lane 1 (TB + d1T, wB + d1W), lane 0 is
+    // the exact base
     long long dT = 0, d1T = 0;
     int dW = 0, d1W = 0;
     if (countB > 0) {
@@ -1543,186 +1554,151 @@ mm_delta_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, MmTra
         d1T = dT + dW;
         d1W = dW;
     }
-    bool merged = false, bail = false, done = false;
+    bool bail = false, done = false;
 
     for (;;) {
+        // merged with the trajectory in place: same state before symbol m, same history
+        if (m >= 2 && same1 && same2 && m < countB) {
+            const int4 b = s_tr[m & RM];
+            if ((((long long)b.x << 32) + (unsigned)b.y) == Tb && b.z == wb) break;
+        }
         if (iters > 64 + (m >> 3)) { bail = true; break; }
         iters++;
-        const int r = (t - tb) & M;
         float2 *sp = s_p[par];
-        unsigned char *ssame = s_same[par];
         // ---- 1. believed state and its interpolant
-        long long TB = MM_NOSTATE;   // the state in place at this lane's symbol
-        int wB = 0, iiB = 0, kB = -1;
-        float2 p0B = make_float2(0.f, 0.f);
-        if (m + r < countB) {
-            const int4 b = s_tr[(m + r) & RM];
-            p0B = s_pb[(m + r) & RM];
-            iiB = b.x;
-            wB = b.z;
-            TB = ((long long)b.x << 32) + (unsigned)b.y;
-            kB = (int)rintf(((float)(unsigned)b.y * MM_UNFIX) * (float)MM_NSTEPS);
-        }
-        long long T;
-        int w;
-        bool valid = true;
-        if (r == 0) { T = Tb; w = wb; }
-        else if (TB != MM_NOSTATE) {
-            if (r == 1) { T = TB + d1T; w = wB + d1W; }
-            else { T = TB + dT + (long long)r * dW; w = wB + dW; }
-        } else { T = 0; w = 0; valid = false; }
+        const int s = m + t;
+        const bool hasB = s < countB;
+        const int4 b = s_tr[s & RM];
+        const float2 p0B = s_pb[s & RM];
+        const long long TB = ((long long)b.x << 32) + (unsigned)b.y;
+        long long T = TB + ((t == 1) ? d1T : dT + (long long)t * dW);
+        int w = b.z + ((t == 1) ? d1W : dW);
+        if (t == 0) { T = Tb; w = wb; }
+        bool valid = hasB || (t == 0);
         const int ii = (int)(T >> 32);
         const unsigned fr = (unsigned)T;
         const float mu = (float)fr * MM_UNFIX;
         const float om = fmaf((float)w, MM_UNFIX, omid);   // exact
         const int k = (int)rintf(mu * (float)MM_NSTEPS);
         const bool stopc = valid && ((ii > last_ok) || (ii >= seg1));
-        const bool match = valid && TB != MM_NOSTATE && ii == iiB && k == kB;
-        float2 p0;
-        if (match) p0 = p0B;
-        else if (valid && !stopc && ii >= lo_min && ii >= xf[0] - RX && ii + MM_NTAPS <= xf[4]) {
-            float ar[4], ai[4];
+        const bool match = hasB && ii == b.x && k == b.w;
+        float2 p0 = p0B;
+        if (!match) {
+            if (valid && !stopc && ii >= lo_min && ii >= xf[0] - RX && ii + MM_NTAPS <= xf[4]) {
+                float ar[4], ai[4];
 #pragma unroll
-            for (int l = 0; l < 4; l++) {
-                const float t0 = s_tab[(7 - l) * 129 + k];
-                const float t1 = s_tab[(3 - l) * 129 + k];
-                const float2 a = s_x[(ii + l) & RXM], bb = s_x[(ii + l + 4) & RXM];
-                ar[l] = fmaf(t1, bb.x, t0 * a.x);
-                ai[l] = fmaf(t1, bb.y, t0 * a.y);
+                for (int l = 0; l < 4; l++) {
+                    const float t0 = s_tab[(7 - l) * 129 + k];
+                    const float t1 = s_tab[(3 - l) * 129 + k];
+                    const float2 a = s_x[(ii + l) & RXM], bb = s_x[(ii + l + 4) & RXM];
+                    ar[l] = fmaf(t1, bb.x, t0 * a.x);
+                    ai[l] = fmaf(t1, bb.y, t0 * a.y);
+                }
+                p0 = make_float2((ar[0] + ar[1]) + (ar[2] + ar[3]), (ai[0] + ai[1]) + (ai[2] + ai[3]));
+                atomicAdd(&s_fresh, 1);
+            } else {
+                p0 = make_float2(0.f, 0.f);
+                if (!stopc) valid = false;
             }
-            p0 = make_float2((ar[0] + ar[1]) + (ar[2] + ar[3]), (ai[0] + ai[1]) + (ai[2] + ai[3]));
-            atomicAdd(&s_fresh, 1);
-        } else {
-            p0 = make_float2(0.f, 0.f);
-            if (!stopc) valid = false;
         }
         sp[t] = p0;
-        ssame[t] = (TB != MM_NOSTATE) && __float_as_uint(p0.x) == __float_as_uint(p0B.x) &&
-                   __float_as_uint(p0.y) == __float_as_uint(p0B.y);
         __syncthreads();   // S1
-        // merged with the trajectory in place: same state before symbol m, same history
-        if (m >= 2 && same1 && same2 && m < countB) {
-            const int4 b = s_tr[m & RM];
-            if ((((long long)b.x << 32) + (unsigned)b.y) == Tb && b.z == wb) { merged = true; break; }
-        }
-        // ---- 2. literal loop update
-        float2 p1 = sp[(t - 1) & M], p2 = sp[(t - 2) & M];
-        if (r == 0) { p1 = P1; p2 = P2; }
-        if (r == 1) { p2 = P1; }
+        // ---- 2. literal loop update, compared with the belief of the next lane
+        float2 p1 = P1, p2 = P2;
+        if (t >= 1) { p1 = sp[t - 1]; p2 = P1; }
+        if (t >= 2) p2 = sp[t - 2];
         float mu2 = mu, om2 = om;
         long long adv = 0;
         mm_update(prm, p0, p1, p2, mu2, om2, adv);
         const long long nT = ((long long)(ii + (int)adv) << 32) + (unsigned)(mu2 * MM_FIX);
         const int nw = (int)((om2 - omid) * MM_FIX);
-        s_nT[t] = valid ? nT : MM_NOSTATE;
-        s_nW[t] = nw;
-        __syncthreads();   // S2
-        // ---- 3. literal acceptance: a lane is good if it could evaluate and its belief IS its predecessor's result
-        bool ok = valid;
-        {
-            long long jT = 0;
-            int jW = 0;
-            if (r > 0) {
-                const int tp = (t - 1) & M;
-                const long long pT = s_nT[tp];
-                if (valid && pT != MM_NOSTATE) {
-                    jT = pT - T;
-                    jW = s_nW[tp] - w;
-                    ok = (jT == 0) && (jW == 0);
-                } else {
-                    jT = MM_NOSTATE;
-                    ok = false;
-                }
-            }
-            s_jT[t] = jT;
-            s_jW[t] = jW;
+        long long jT = MM_NOSTATE;
+        int jW = 0;
+        bool next_ok = false;
+        if (valid && s + 1 < countB) {
+            const int4 bn = s_tr[(s + 1) & RM];
+            const long long TBn = ((long long)bn.x << 32) + (unsigned)bn.y;
+            const long long Tn = TBn + ((t == 0) ? d1T : dT + (long long)(t + 1) * dW);
+            const int wn = bn.z + ((t == 0) ? d1W : dW);
+            jT = nT - Tn;
+            jW = nw - wn;
+            next_ok = (jT == 0) && (jW == 0);
         }
-        const unsigned m0 = __reduce_min_sync(0xffffffffu, ok ? (unsigned)NT : (unsigned)r);
-        const unsigned m1 = __reduce_min_sync(0xffffffffu, stopc ? (unsigned)r : (unsigned)NT);
+        s_nT[t] = nT;
+        s_nW[t] = nw;
+        s_jT[t] = jT;
+        s_jW[t] = jW;
+        s_same[t] = hasB && __float_as_uint(p0.x) == __float_as_uint(p0B.x) && __float_as_uint(p0.y) == __float_as_uint(p0B.y);
+        // first lane that is not exact: lane r + 1 if its belief is not this lane's result, lane r if it could not evaluate
+        const unsigned c0 = !valid ? (unsigned)t : (!next_ok ? (unsigned)(t + 1) : (unsigned)NT);
+        const unsigned m0 = __reduce_min_sync(0xffffffffu, c0);
+        const unsigned m1 = __reduce_min_sync(0xffffffffu, stopc ? (unsigned)t : (unsigned)NT);
         if ((t & 31) == 0) {
             if (m0 < NT) atomicMin(&s_min[par][0], m0);
             if (m1 < NT) atomicMin(&s_min[par][1], m1);
         }
-        __syncthreads();   // S3
+        __syncthreads();   // S2
         const int fb = (int)s_min[par][0];        // first lane that is not exact (>= 1: the base always is)
         const int r_stop = (int)s_min[par][1];
         if (fb == 0) { bail = true; break; }      // the base could not be evaluated (cannot happen for a state in range)
         const bool stop = r_stop < fb;            // an exact lane is past the segment
         const int hi = stop ? r_stop : fb;
-        if (r < hi) {
-            const int pos = m + r;
-            if (pos < cap_seg) {
-                if (!match) stage[pos] = p0;
-                if (TB == MM_NOSTATE || T != TB || w != wB) tr.rec[pos] = make_int4(ii, (int)fr, w, 0);
+        if (t < hi) {
+            if (s < cap_seg) {
+                if (!match) stage[s] = p0;
+                if (!hasB || T != TB || w != b.z) tr.rec[s] = make_int4(ii, (int)fr, w, k);
             } else overflow = 1;
         }
         if (stop) {
-            if (r == r_stop) {
-                float2 q1 = sp[(t - 1) & M], q2 = sp[(t - 2) & M];
-                if (r == 0) { q1 = P1; q2 = P2; }
-                if (r == 1) { q2 = P1; }
-                MmState s;
-                s.ii = ii;
-                s.mu = mu;
-                s.omega = om;
-                s.p0 = q1;
-                s.p1 = q2;
-                exit_[j] = s;
+            if (t == r_stop) {
+                MmState so;
+                so.ii = ii;
+                so.mu = mu;
+                so.omega = om;
+                so.p0 = p1;   // interpolants of the two symbols before this lane's
+                so.p1 = p2;
+                exit_[j] = so;
             }
             m += hi;
             done = true;
             break;
         }
-        // ---- 4. slide by fb: lane fb - 1's result is the new exact base
-        const int tl = (tb + fb - 1) & M;
-        const long long nTb = s_nT[tl];
-        const int nwb = s_nW[tl];
+        // ---- 3. slide by fb: lane fb - 1's result is the new exact base
+        Tb = s_nT[fb - 1];
+        wb = s_nW[fb - 1];
         if (fb >= 2) {
-            const int t2 = (tb + fb - 2) & M;
-            P2 = sp[t2];
-            P1 = sp[tl];
-            same2 = ssame[t2] != 0;
-            same1 = ssame[tl] != 0;
+            P2 = sp[fb - 2];
+            P1 = sp[fb - 1];
+            same2 = s_same[fb - 2] != 0;
+            same1 = s_same[fb - 1] != 0;
         } else {
             P2 = P1;
-            P1 = sp[tb];
+            P1 = sp[0];
             same2 = same1;
-            same1 = ssame[tb] != 0;
+            same1 = s_same[0] != 0;
         }
-        // re-fit the offsets from the jumps measured at lanes fb, fb + 1, fb + 2
+        // re-fit the offsets from the jumps measured at lanes fb, fb + 1, fb + 2 (published by the lane before each)
         {
-            long long a0 = 0, a1 = 0, a2 = 0;
-            int b0 = 0, b1 = 0, b2 = 0;
-            if (fb < NT) {
-                const int tf = (tb + fb) & M;
-                if (s_jT[tf] != MM_NOSTATE) { a0 = s_jT[tf]; b0 = s_jW[tf]; }
-                if (fb + 1 < NT) {
-                    const int tf1 = (tf + 1) & M;
-                    if (s_jT[tf1] != MM_NOSTATE) { a1 = s_jT[tf1]; b1 = s_jW[tf1]; }
-                }
-                if (fb + 2 < NT) {
-                    const int tf2 = (tf + 2) & M;
-                    if (s_jT[tf2] != MM_NOSTATE) { a2 = s_jT[tf2]; b2 = s_jW[tf2]; }
-                }
-            }
-            // lane fb + 1 had believed TB + dT + (fb + 1) * dW (fb >= 1, so it was not lane 1)
+            long long a0 = s_jT[fb - 1], a1 = 0, a2 = 0;
+            int b0 = s_jW[fb - 1], b1 = 0, b2 = 0;
+            if (a0 == MM_NOSTATE) { a0 = 0; b0 = 0; }
+            if (fb < NT && s_jT[fb] != MM_NOSTATE) { a1 = s_jT[fb]; b1 = s_jW[fb]; }
+            if (fb + 1 < NT && s_jT[fb + 1] != MM_NOSTATE) { a2 = s_jT[fb + 1]; b2 = s_jW[fb + 1]; }
+            // (jumps are measured against the beliefs actually held, and lanes fb + 1.. held the general one, so these
+            // sums are right whichever offsets lane fb itself had)
             d1T = dT + (long long)(fb + 1) * dW + a0 + a1 + b0;
             d1W = dW + b0 + b1;
             dT = dT + (long long)fb * dW + a0 + a1 + a2 - ((long long)b1 + 2LL * (long long)b2);
             dW = dW + b0 + b1 + b2;
         }
-        tb = (tb + fb) & M;
         m += fb;
-        Tb = nTb;
-        wb = nwb;
         if (t < 2) s_min[par ^ 1][t] = NT;
         par ^= 1;
         // slots of symbols below the new base are free: stream in up to m + R.  Every thread then waits for all of its
-        // groups but the three newest (DRAM latency spans several iterations); the barriers of the next iteration
-        // publish them, so the window after that reads nothing above (base four slides ago) + R >= its own base + 2 NT
-        // (a slide is at most NT; R = 8 NT).
+        // groups but the three newest; the barriers of the next iteration publish them, so the window after that reads
+        // nothing above (base four slides ago) + R >= its own base + 2 NT (a slide is at most NT; R = 8 NT).
         xf[4] = xf[3]; xf[3] = xf[2]; xf[2] = xf[1]; xf[1] = xf[0];
-        refill(m + R, (int)(Tb >> 32));
+        refill(m, (int)(Tb >> 32));
         asm volatile("cp.async.wait_group 3;\n" ::: "memory");
     }
     cp_async_wait_all();
@@ -1749,7 +1725,6 @@ mm_delta_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, MmTra
         segout[j] = so;
         redo[j] = 0;
     }
-    (void)merged;
 }
 
 // hand-off check for M&M: redo[j] = entry[j] != exit[j-1] (then entry[j] := exit[j-1])
