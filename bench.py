@@ -274,7 +274,7 @@ def run_b200(args):
     # together, so the PCIe copies of one step overlap the kernels of the other (and its kernels fill the SMs the
     # other's certified re-run rounds leave idle).  Every step still copies its 1 GB in and its symbols out inside
     # the timed region and starts from the freshly constructed loop state.
-    e2e_ms, in_flight = e2e_seq_ms, 1
+    e2e_ms, in_flight, e2e_i8_ms = e2e_seq_ms, 1, None
     if not args.no_overlap:
         nf = max(2, args.in_flight)
         extra = [demod.Demodulator(mode="hrit", device_ordinal=local) for _ in range(nf - 1)]
@@ -282,13 +282,15 @@ def run_b200(args):
         per_handle = max(2, ke)
         counts = [[] for _ in handles]
 
+        api = [demod.lib().xrd_demod_batch]
+
         def work(i):
             dd, hs = handles[i]
             cnt = np.zeros(1, np.int64)
             for _ in range(per_handle):
                 dd.reset()
-                rcode = demod.lib().xrd_demod_batch(dd._h, C.c_void_p(h_in.data_ptr()), n, 0, C.c_void_p(hs.data_ptr()),
-                                                    cap, cnt.ctypes.data_as(C.POINTER(C.c_int64)))
+                rcode = api[0](dd._h, C.c_void_p(h_in.data_ptr()), n, 0, C.c_void_p(hs.data_ptr()),
+                               cap, cnt.ctypes.data_as(C.POINTER(C.c_int64)))
                 counts[i].append((rcode, int(cnt[0])))
 
         def run_pair():
@@ -308,6 +310,19 @@ def run_b200(args):
         for _, hs in handles[1:]:
             assert torch.equal(h_sym[: 2 * nsym], hs[: 2 * nsym])
         e2e_ms, in_flight = tot_ms / done, nf
+        # the same with the reference's own egress format: int8 soft symbols packed by the last kernel
+        # (xrd_demod_batch_i8, SymbolManager.cpp:43-46), 1 byte per symbol back over PCIe instead of 8
+        api[0] = demod.lib().xrd_demod_batch_i8
+        counts = [[] for _ in handles]
+        run_pair()
+        counts = [[] for _ in handles]
+        shard.barrier()
+        tot_i8 = run_pair()
+        done_i8 = sum(len(c) for c in counts)
+        assert all(rc == 0 and ns == nsym for c in counts for rc, ns in c), counts
+        soft = h_sym.view(torch.int8)[:nsym].to(torch.int32)
+        assert (int(soft.sum().item()) & 0xFFFFFFFF) == checksum, "int8 egress checksum"
+        e2e_i8_ms = tot_i8 / done_i8
         for dx in extra:
             dx.close()
 
@@ -365,6 +380,9 @@ def run_b200(args):
         "e2e": {"value": agg_e["msps"], "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * nsym,
                 "ms_per_step": agg_e["elapsed_ms"], "steps_in_flight": in_flight,
                 "one_step_at_a_time": {"value": n / e2e_seq_ms / 1e3, "ms_per_step": e2e_seq_ms},
+                "int8_egress": None if e2e_i8_ms is None else {
+                    "value": n / e2e_i8_ms / 1e3, "ms_per_step": e2e_i8_ms, "d2h_bytes_per_step": nsym,
+                    "note": "xrd_demod_batch_i8: int8 soft symbols (the reference's wire format) packed by the last kernel"},
                 "note": "xrd_demod_batch on pinned host buffers; steps_in_flight = N: consecutive steps run on N demodulator "
                         "handles (N host threads), so the PCIe copies of one step overlap the kernels of the others; every "
                         "step's H2D and D2H are inside the timed region"},

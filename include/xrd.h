@@ -97,6 +97,13 @@ int xrd_demod_batch(xrd_demod *d, const void *iq, size_t n_complex, int type, fl
 int xrd_demod_device(xrd_demod *d, const void *iq_dev, size_t n_complex, int type, float *sym_dev, size_t cap,
                      int64_t *n_sym);
 
+/* xrd_demod_batch with the egress of SymbolManager::process (SymbolManager.cpp:37-52) fused into the last kernel:
+ * soft_out[channel * cap ...] receives one int8 soft symbol per recovered symbol (Re(s)*127, clamp [-128,127],
+ * C cast) -- the byte stream the reference sends to the decoder (decoder/src/newdecoder.cpp:213-216 reads it in
+ * 16384-byte frames).  No cf32 symbols cross PCIe: 1 byte per symbol instead of 8. */
+int xrd_demod_batch_i8(xrd_demod *d, const void *iq, size_t n_complex, int type, int8_t *soft_out, size_t cap,
+                       int64_t *n_sym);
+
 /* int8 soft symbols == SymbolManager::process   SymbolManager.cpp:43-46
  * (Re(s)*127, clamp [-128,127], C cast).  Host buffers. */
 int xrd_soft_i8(xrd_demod *d, const float *sym_cf32, size_t n_symbols, int8_t *out);

@@ -323,6 +323,22 @@ def test_soft_i8_egress(gpu, xrd, oracle, stages):
     np.testing.assert_array_equal(d.soft_i8(edge), oracle.soft_i8(edge))
 
 
+@pytest.mark.parametrize("mode", ["hrit", "lrit"])
+def test_fused_i8_egress(gpu, xrd, oracle, mode):
+    """xrd_demod_batch_i8: the bytes of SymbolManager::process packed by the last kernel of the chain equal the
+    oracle's symbols through the oracle's byte rule; two calls, state carried, two channels"""
+    _, x0 = make_signal(mode, 1 << 20)
+    _, x1 = make_signal(mode, 1 << 20, channel=1)
+    hrit = mode == "hrit"
+    refs = [oracle.soft_i8(oracle.Chain(oracle.config(hrit)).process(x)) for x in (x0, x1)]
+    d = xrd.Demodulator(mode=mode, n_channels=2)
+    half = (1 << 19) + 4321
+    a = d.demod_i8(np.stack([x0[:half], x1[:half]]))
+    b = d.demod_i8(np.stack([x0[half:], x1[half:]]))
+    for c in range(2):
+        np.testing.assert_array_equal(np.concatenate([a[c], b[c]]), refs[c])
+
+
 def test_full_size_stream_properties(gpu, xrd, oracle):
     """configs[1] at full size (125 000 000 samples, 1 GB): one-shot == chunked (chunk invariance,
     a size-independent property), symbol count within the timing-loop bounds, and the oracle on

@@ -520,6 +520,7 @@ struct MmStage {
     uint64_t bails = 0;             // delta re-runs that gave up and fell back to the chain kernel
     int ck_spacing = 65536;         // samples between chain checkpoints
     int *h_nredo = nullptr;
+    signed char *out_i8 = nullptr;  // when set, the compaction also (out != null) or only (out == null) emits int8 soft symbols
     std::vector<long long> h_offsets;
     uint64_t rounds = 0, redone = 0, windows = 0, iters = 0;
 
@@ -736,7 +737,7 @@ struct MmStage {
         const int parts = std::max(1, std::min(64, (sm_count * 16) / std::max(1, nseg * nch)));
         dim3 cg((unsigned)nseg * parts, nch);
         XRD_LAUNCH(c, mm_compact_kernel, cg, 256, 0, st, d_stage.as<float2>(), out, nseg, cap_seg,
-                   d_segout.as<MmSegOut>(), d_offsets.as<long long>(), out_cap, stage_stride, out_stride);
+                   d_segout.as<MmSegOut>(), d_offsets.as<long long>(), out_cap, stage_stride, out_stride, out_i8);
         XRD_LAUNCH(c, mm_rebase_kernel, (nch + 127) / 128, 128, 0, st, d_carried.as<MmState>(), d_exit.as<MmState>(),
                    nseg, nch, n);
         h_offsets.resize((size_t)(nseg + 1) * nch);
@@ -1221,6 +1222,34 @@ int xrd_demod_batch(xrd_demod *d, const void *iq, size_t n_complex, int type, fl
             const size_t cnt = (size_t)std::min<long long>(n_sym[ch], (long long)cap);
             XRD_CUDA(cudaMemcpyAsync(sym_out + 2 * cap * ch, d->b_sym.as<float2>() + cap * ch, sizeof(float2) * cnt,
                                      cudaMemcpyDeviceToHost, d->stream));
+        }
+        XRD_CUDA(cudaStreamSynchronize(d->stream));
+        return rc;
+    });
+}
+
+int xrd_demod_batch_i8(xrd_demod *d, const void *iq, size_t n_complex, int type, int8_t *soft_out, size_t cap,
+                       int64_t *n_sym)
+{
+    if (!d || !iq || !soft_out || !n_sym || !type_bytes(type)) return XRD_E_ARG;
+    return guarded(&d->err, [&]() {
+        XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
+        d->b_i8.ensure(cap * d->nch);
+        // the M&M compaction writes the bytes itself; no cf32 symbol stream is materialised
+        d->mm.out_i8 = d->b_i8.as<signed char>();
+        int rc;
+        try {
+            rc = d->run_host(iq, (long long)n_complex, type, nullptr, (long long)cap, n_sym);
+        } catch (...) {
+            d->mm.out_i8 = nullptr;
+            throw;
+        }
+        d->mm.out_i8 = nullptr;
+        if (rc != XRD_OK && rc != XRD_E_OVERFLOW) return rc;
+        for (int ch = 0; ch < d->nch; ch++) {
+            const size_t cnt = (size_t)std::min<long long>(n_sym[ch], (long long)cap);
+            XRD_CUDA(cudaMemcpyAsync(soft_out + cap * ch, d->b_i8.as<signed char>() + cap * ch, cnt, cudaMemcpyDeviceToHost,
+                                     d->stream));
         }
         XRD_CUDA(cudaStreamSynchronize(d->stream));
         return rc;

@@ -1749,14 +1749,26 @@ __global__ void mm_verify_kernel(int nseg, MmState *__restrict__ entry, const Mm
     if (r) atomicAdd(n_redo, 1);
 }
 
-// gather the per-segment staging slots into the contiguous symbol stream
+// int8 soft symbol (SymbolManager::process, reference SymbolManager.cpp:43-46): f = Re(s)*127, clamp to [-128, 127],
+// C cast (truncation toward zero)
+__device__ __forceinline__ signed char soft_i8(float re)
+{
+    float f = re * 127.f;
+    f = f > 127.f ? 127.f : f;
+    f = f < -128.f ? -128.f : f;
+    return (signed char)(int)f;
+}
+
+// gather the per-segment staging slots into the contiguous symbol stream (cf32 and / or int8 soft symbols)
 __global__ void mm_compact_kernel(const float2 *__restrict__ stage, float2 *__restrict__ out, int nseg, long long cap_seg,
                                   const MmSegOut *__restrict__ segout, long long *__restrict__ offsets /* [nseg+1] */,
-                                  long long out_cap, long long stage_ch_stride, long long out_ch_stride)
+                                  long long out_cap, long long stage_ch_stride, long long out_ch_stride,
+                                  signed char *__restrict__ out_i8)
 {
     const int ch = blockIdx.y;
     stage += (size_t)ch * stage_ch_stride;
-    out += (size_t)ch * out_ch_stride;
+    if (out) out += (size_t)ch * out_ch_stride;
+    if (out_i8) out_i8 += (size_t)ch * out_ch_stride;
     segout += (size_t)ch * nseg;
     offsets += (size_t)ch * (nseg + 1);
     // blockIdx.x = segment * parts + part: every segment is copied by `parts` CTAs so that the grid fills the GPU
@@ -1767,7 +1779,11 @@ __global__ void mm_compact_kernel(const float2 *__restrict__ stage, float2 *__re
     const int c = segout[j].n_sym;
     const float2 *src = stage + (size_t)j * cap_seg;
     for (long long i = (long long)part * blockDim.x + threadIdx.x; i < c; i += (long long)parts * blockDim.x)
-        if (o + i < out_cap) out[o + i] = src[i];
+        if (o + i < out_cap) {
+            const float2 v = src[i];
+            if (out) out[o + i] = v;
+            if (out_i8) out_i8[o + i] = soft_i8(v.x);   // the byte SymbolManager::process sends (SymbolManager.cpp:43-46)
+        }
 }
 
 __global__ void mm_offsets_kernel(int nseg, const MmSegOut *__restrict__ segout, long long *__restrict__ offsets,
@@ -1795,12 +1811,7 @@ __global__ void soft_i8_kernel(const float2 *__restrict__ sym, signed char *__re
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        float f = sym[i].x * 127.f;
-        f = f > 127.f ? 127.f : f;
-        f = f < -128.f ? -128.f : f;
-        out[i] = (signed char)(int)f;
-    }
+    for (; i < n; i += stride) out[i] = soft_i8(sym[i].x);
 }
 
 }  // namespace xrd

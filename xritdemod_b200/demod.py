@@ -26,7 +26,7 @@ _NP_OF_TYPE = {XRD_FLOATIQ: np.float32, XRD_S16IQ: np.int16, XRD_S8IQ: np.int8}
 # every symbol include/xrd.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "xrd_config_defaults", "xrd_create", "xrd_destroy", "xrd_last_error", "xrd_add_samples", "xrd_process",
-    "xrd_demod_batch", "xrd_demod_device", "xrd_soft_i8", "xrd_get_state", "xrd_reset", "xrd_stream", "xrd_set_tuning", "xrd_get_stats",
+    "xrd_demod_batch", "xrd_demod_batch_i8", "xrd_demod_device", "xrd_soft_i8", "xrd_get_state", "xrd_reset", "xrd_stream", "xrd_set_tuning", "xrd_get_stats",
     "xrd_design_rrc", "xrd_design_lowpass", "xrd_mmse_table", "xrd_costas_gains",
     "xrd_fir_create", "xrd_agc_create", "xrd_costas_create", "xrd_clock_recovery_create", "xrd_stage_work",
     "xrd_stage_set_tuning", "xrd_stage_set_loop_kernel", "xrd_stage_destroy", "xrd_stage_last_error", "xrd_device_check", "xrd_version",
@@ -108,6 +108,7 @@ def lib():
     L.xrd_process.argtypes = [vp, C.c_int64, SYMBOLS_CB, vp]
     L.xrd_process.restype = C.c_int64
     L.xrd_demod_batch.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, i64p]
+    L.xrd_demod_batch_i8.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, i64p]
     L.xrd_demod_device.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, i64p]
     L.xrd_soft_i8.argtypes = [vp, vp, C.c_size_t, vp]
     L.xrd_get_state.argtypes = [vp, C.c_int, C.POINTER(LoopState)]
@@ -374,6 +375,21 @@ class Demodulator:
         cnt = np.zeros(self.n_channels, np.int64)
         self._check(lib().xrd_demod_batch(self._h, _p(a), n, type, _p(sym), cap, cnt.ctypes.data_as(C.POINTER(C.c_int64))))
         outs = [sym[c, : 2 * cnt[c]].view(np.complex64).copy() for c in range(self.n_channels)]
+        return outs[0] if self.n_channels == 1 else outs
+
+    def demod_i8(self, iq, type=XRD_FLOATIQ):
+        """as demod(), but returns the int8 soft symbols the reference puts on the wire (SymbolManager.cpp:43-46),
+        packed by the last kernel of the chain"""
+        if type == XRD_FLOATIQ:
+            a = _iq(iq)
+        else:
+            a = np.ascontiguousarray(iq, _NP_OF_TYPE[type]).reshape(-1)
+        n = len(a) // 2 // self.n_channels
+        cap = self.symbol_capacity(n)
+        soft = np.empty((self.n_channels, cap), np.int8)
+        cnt = np.zeros(self.n_channels, np.int64)
+        self._check(lib().xrd_demod_batch_i8(self._h, _p(a), n, type, _p(soft), cap, cnt.ctypes.data_as(C.POINTER(C.c_int64))))
+        outs = [soft[c, : cnt[c]].copy() for c in range(self.n_channels)]
         return outs[0] if self.n_channels == 1 else outs
 
     def demod_device(self, iq_ptr, n_complex, sym_ptr, cap, type=XRD_FLOATIQ):
