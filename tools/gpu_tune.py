@@ -7,7 +7,7 @@ import numpy as np, torch
 from xritdemod_b200 import demod, siggen
 
 n = int(sys.argv[1])
-p = siggen.params("hrit", 0, n=n, ramp_len=1 << 20)
+p = siggen.params("hrit", int(os.environ.get("CHANNEL", "0")), n=n, ramp_len=1 << 20)
 h = torch.empty(2 * n, dtype=torch.float32).pin_memory()
 siggen.generate(p, n, out=h.numpy().view(np.complex64))
 x = h.cuda()

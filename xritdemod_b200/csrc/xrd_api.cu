@@ -306,7 +306,8 @@ template <class LOOP> struct SegStage {
     int redo_variant = 4; // kernel of the certified re-runs: few chains, so the widest window (fastest single chain) wins
     bool use_mirror = false;
     int nch = 1, sm_count = 148;
-    DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list, d_ckpt, d_iters, d_psi, d_adv;
+    DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list, d_ckpt, d_iters, d_psi, d_adv, d_pre, d_adv0;
+    int pre_len = 0;          // Costas: samples of segment 0 run ahead of the branch resolution (0: none)
     int *h_nredo = nullptr;   // pinned
     uint64_t rounds = 0, redone = 0, escalations = 0;
     State s_init;
@@ -351,7 +352,8 @@ template <class LOOP> struct SegStage {
     void resolve_impl(Counters &c, cudaStream_t st, int nseg, int Ls, long long Ws, CostasState *e)
     {
         XRD_LAUNCH(c, costas_resolve_kernel, nch, 256, sizeof(unsigned) * ((nseg + 31) / 32), st, nseg, Ls, Ws, e,
-                   d_adv.as<float>(), (int *)nullptr);
+                   d_adv.as<float>(), (int *)nullptr, pre_len > 0 ? d_pre.as<CostasState>() : (const CostasState *)nullptr,
+                   pre_len > 0 ? d_adv0.as<float>() : (const float *)nullptr);
     }
     void resolve_impl(Counters &, cudaStream_t, int, int, long long, AgcState *) {}
 
@@ -377,7 +379,7 @@ template <class LOOP> struct SegStage {
             XRD_LAUNCH(c, (wn_loop_kernel<LOOP, WN_K>), grid, WN_WARPS * 32, wn_smem_bytes<WN_K>(), st, in, out, n, Ls, Ws, nseg,
                        n_work, d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(),
                        d_ckpt.as<State>(), ncp, WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride,
-                       hist);
+                       hist, (mode == 2 && pre_len > 0) ? d_pre.as<State>() : (State *)nullptr, pre_len);
         } else {
             const int grid = (n_work + SEG_NTH - 1) / SEG_NTH;
             XRD_LAUNCH(c, (seg_loop_kernel<LOOP, SEG_TS>), grid, SEG_NTH, 0, st, in, out, n, Ls, Ws, nseg, n_work,
@@ -423,7 +425,14 @@ template <class LOOP> struct SegStage {
             if (use_mirror) d_mirror.ensure(tot);
             if (wn) d_ckpt.ensure(sizeof(State) * tot * ncp);
             if (wn && use_mirror && nseg > 1 && n >= 2 * CPB) {
-                // Costas: warm-ups, then put the entry states on one carrier-phase branch, then the segments
+                // Costas: warm-ups, then put the entry states on one carrier-phase branch, then the segments.
+                // Segment 0 has no warm-up; the window kernel runs its first pre_len samples beside the others'
+                // warm-ups so that the resolution can refer to the branch the true trajectory acquires on.
+                pre_len = (wn_variant == 2 && hist == 0) ? std::min(Ws, Ls) / CPB * CPB : 0;
+                if (pre_len > 0) {
+                    d_pre.ensure(sizeof(State) * nch);
+                    d_adv0.ensure(sizeof(float) * nch);
+                }
                 launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 2, in_stride, out_stride);
                 const long long nblk = n / CPB;
                 d_psi.ensure(sizeof(float) * (size_t)nblk * nch);
@@ -432,7 +441,7 @@ template <class LOOP> struct SegStage {
                 XRD_LAUNCH(c, costas_block_phase_kernel, g1, 256, 0, st, in, d_psi.as<float>(), nblk, in_stride, nblk);
                 dim3 g2(nseg, nch);
                 XRD_LAUNCH(c, costas_seg_advance_kernel, g2, 256, 0, st, d_psi.as<float>(), d_adv.as<float>(), nseg, Ls / CPB,
-                           nblk, nblk);
+                           nblk, nblk, pre_len > 0 ? d_adv0.as<float>() : (float *)nullptr, pre_len / CPB);
                 resolve(c, st, nseg, Ls, (long long)Ws - hist);
                 launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 3, in_stride, out_stride);
             } else {

@@ -334,7 +334,8 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
                typename LOOP::State *__restrict__ entry, typename LOOP::State *__restrict__ exit_,
                const typename LOOP::State *__restrict__ carried, const int *__restrict__ list,
                typename LOOP::State *__restrict__ ckpt, int ncp, int C, unsigned long long *__restrict__ iters_total,
-               typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride, long long hist)
+               typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride, long long hist,
+               typename LOOP::State *__restrict__ pre, int pre_len)
 {
     extern __shared__ __align__(16) unsigned char wn_smem[];
     typedef typename LOOP::State State;
@@ -368,6 +369,13 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
         }
         if (s_begin < 0) st = wn_run<LOOP, K, false, WN_CK_NONE>(x, y, s_begin, 0, st, prm, ring, nullptr, C, nullptr, &iters);
         if (lane == 0) entry[g] = st;
+        // mode 2, first segment of a channel: it has no warm-up (its entry is the carried state, which right after a
+        // reset is not locked yet), so run its first pre_len samples here, next to the others' warm-ups, and leave the
+        // state reached -- the TRUE trajectory's, acquisition included -- for the branch resolution to refer to
+        if (mode == 2 && pre && j == 0 && pre_len > 0 && pre_len <= len) {
+            const State p = wn_run<LOOP, K, false, WN_CK_NONE>(x, y, 0, pre_len, st, prm, ring, nullptr, C, nullptr, &iters);
+            if (lane == 0) pre[ch] = p;
+        }
     }
     if (mode == 3) st = entry[g];
     if (mode == 0 || mode == 3) {
@@ -739,34 +747,52 @@ costas_block_phase_kernel(const float2 *__restrict__ in, float *__restrict__ psi
 // adv[g] = continuous carrier-phase advance from the start of segment g to the start of segment g+1
 __global__ void __launch_bounds__(256)
 costas_seg_advance_kernel(const float *__restrict__ psi, float *__restrict__ adv, int nseg, int blk_per_seg, long long nblk,
-                          long long psi_ch_stride)
+                          long long psi_ch_stride, float *__restrict__ adv0_tail, int pre_blk)
 {
-    __shared__ double s_part[8];
+    // adv0_tail[ch] (optional) = the part of segment 0's advance from block pre_blk on, i.e. from where the pre-run of
+    // segment 0 stopped (wn_loop_kernel, mode 2) to the start of segment 1
+    __shared__ double s_part[2][8];
     const int j = blockIdx.x, ch = blockIdx.y;
     const float *ps = psi + (size_t)ch * psi_ch_stride;
     const long long b0 = (long long)j * blk_per_seg;
-    double acc = 0.0;
+    double acc = 0.0, tail = 0.0;
     for (long long b = b0 + threadIdx.x; b < b0 + blk_per_seg && b + 1 < nblk; b += blockDim.x) {
         float d = ps[b + 1] - ps[b];
         d = (d > 3.14159265f) ? d - 6.28318531f : ((d < -3.14159265f) ? d + 6.28318531f : d);
         acc += (double)d;
+        if (b - b0 >= pre_blk) tail += (double)d;
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    for (int o = 16; o >= 1; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        tail += __shfl_xor_sync(0xffffffffu, tail, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_part[0][threadIdx.x >> 5] = acc;
+        s_part[1][threadIdx.x >> 5] = tail;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_part[w];
+        double t = 0.0, u = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+            t += s_part[0][w];
+            u += s_part[1][w];
+        }
         adv[(size_t)ch * nseg + j] = (float)(0.5 * t);
+        if (j == 0 && adv0_tail) adv0_tail[ch] = (float)(0.5 * u);
     }
 }
 
 // puts the warm-up entry states of a channel on the branch of segment 0 (which starts from the exact state)
 __global__ void costas_resolve_kernel(int nseg, int L, long long W /* warm-up minus addressable history */,
                                       CostasState *__restrict__ entry, const float *__restrict__ adv,
-                                      int *__restrict__ n_flipped)
+                                      int *__restrict__ n_flipped, const CostasState *__restrict__ pre,
+                                      const float *__restrict__ adv0_tail)
 {
+    // pre (optional): the state the TRUE trajectory reached inside segment 0 (pre-run of wn_loop_kernel, mode 2), with
+    // adv0_tail the carrier advance from there to the start of segment 1: segment 1 is then referred to that instead of
+    // to segment 0's entry, which right after a reset is the unlocked initial state and says nothing about the branch
+    // the loop acquires on
     // flip[j] = entry j lies on the other branch than (entry j-1 advanced by adv[j-1]) -- independent of what
     // happens to j-1, because flipping j-1 by pi flips the prediction by pi too: so the branch of j relative to
     // segment 0 is the running parity of the flips, a prefix XOR done here by warp ballots
@@ -781,7 +807,8 @@ __global__ void costas_resolve_kernel(int nseg, int L, long long W /* warm-up mi
         bool f = false;
         if (j >= 1 && j < nseg) {
             const bool exact = ((long long)j * L - W <= 0);          // ran from the carried state: on the true branch
-            f = !exact && (__cosf(e[j].phase - (e[j - 1].phase + a[j - 1])) < 0.f);
+            const float want = (j == 1 && pre) ? pre[ch].phase + adv0_tail[ch] : e[j - 1].phase + a[j - 1];
+            f = !exact && (__cosf(e[j].phase - want) < 0.f);
         }
         const unsigned m = __ballot_sync(0xffffffffu, f);
         if (lane == 0) s_par[w] = m;
