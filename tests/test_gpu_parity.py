@@ -6,10 +6,12 @@ Bar (BASELINE.json north_star): soft-symbol RMS <= 1e-4.  The chain is chaotic a
 costs ~1e-4 RMS, see DESIGN.md "Why bit-exact"), so these tests assert the stronger property
 the kernels are built for: bit-exact equality with the oracle, which implies RMS == 0.
 """
+import os
+
 import numpy as np
 import pytest
 
-from conftest import assert_bitexact, make_signal
+from conftest import ROOT, assert_bitexact, make_signal
 
 pytestmark = pytest.mark.gpu
 RMS_TOL = 1e-4  # north_star tolerance on Re(symbol)
@@ -337,6 +339,24 @@ def test_fused_i8_egress(gpu, xrd, oracle, mode):
     b = d.demod_i8(np.stack([x0[half:], x1[half:]]))
     for c in range(2):
         np.testing.assert_array_equal(np.concatenate([a[c], b[c]]), refs[c])
+
+
+def test_cfile_tool(gpu, xrd, oracle, tmp_path):
+    """tools/demod_cfile.py: a recorded cfile through the chain in ragged chunks gives the oracle's soft bytes"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("demod_cfile", os.path.join(ROOT, "tools", "demod_cfile.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    _, x = make_signal("hrit", 600000)
+    ref = oracle.soft_i8(oracle.Chain(oracle.config(True)).process(x))
+    src, dst = tmp_path / "in.cfile", tmp_path / "out.s8"
+    np.ascontiguousarray(x, np.complex64).tofile(src)
+    n_in, n_sym = tool.main([str(src), str(dst), "--chunk", "200001"])
+    assert n_in == len(x) and n_sym == len(ref)
+    np.testing.assert_array_equal(np.fromfile(dst, np.int8), ref)
+    dst2 = tmp_path / "out2.s8"
+    tool.main([str(src), str(dst2), "--chunk", "333333", "--cf32-out", str(tmp_path / "sym.cf32")])
+    np.testing.assert_array_equal(np.fromfile(dst2, np.int8), ref)
 
 
 def test_full_size_stream_properties(gpu, xrd, oracle):
