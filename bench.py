@@ -274,7 +274,7 @@ def run_b200(args):
     # together, so the PCIe copies of one step overlap the kernels of the other (and its kernels fill the SMs the
     # other's certified re-run rounds leave idle).  Every step still copies its 1 GB in and its symbols out inside
     # the timed region and starts from the freshly constructed loop state.
-    e2e_ms, in_flight, e2e_i8_ms, dev_conc_ms = e2e_seq_ms, 1, None, None
+    e2e_ms, in_flight, e2e_i8_ms, dev_conc_ms, e2e_s16_ms = e2e_seq_ms, 1, None, None, None
     if not args.no_overlap:
         nf = max(2, args.in_flight)
         extra = [demod.Demodulator(mode="hrit", device_ordinal=local) for _ in range(nf - 1)]
@@ -282,14 +282,14 @@ def run_b200(args):
         per_handle = max(2, ke)
         counts = [[] for _ in handles]
 
-        api = [demod.lib().xrd_demod_batch]
+        api = [demod.lib().xrd_demod_batch, h_in.data_ptr(), 0]   # entry point, input buffer, sample type
 
         def work(i):
             dd, hs = handles[i]
             cnt = np.zeros(1, np.int64)
             for _ in range(per_handle):
                 dd.reset()
-                rcode = api[0](dd._h, C.c_void_p(h_in.data_ptr()), n, 0, C.c_void_p(hs.data_ptr()),
+                rcode = api[0](dd._h, C.c_void_p(api[1]), n, api[2], C.c_void_p(hs.data_ptr()),
                                cap, cnt.ctypes.data_as(C.POINTER(C.c_int64)))
                 counts[i].append((rcode, int(cnt[0])))
 
@@ -323,6 +323,23 @@ def run_b200(args):
         soft = h_sym.view(torch.int8)[:nsym].to(torch.int32)
         assert (int(soft.sum().item()) & 0xFFFFFFFF) == checksum, "int8 egress checksum"
         e2e_i8_ms = tot_i8 / done_i8
+        # and with the reference's usual ingest format as well (S16 IQ from the SDR front ends, demodulator.cpp:57-63):
+        # the same stream quantised to int16, 4 bytes per sample in, 1 byte per symbol out
+        h_in16 = torch.empty(2 * n, dtype=torch.int16).pin_memory()
+        for c0 in range(0, 2 * n, 1 << 24):
+            c1 = min(2 * n, c0 + (1 << 24))
+            h_in16[c0:c1] = torch.clamp(torch.round(h_in[c0:c1] * 32768.0), -32768, 32767).to(torch.int16)
+        api[1], api[2] = h_in16.data_ptr(), 1
+        counts = [[] for _ in handles]
+        run_pair()
+        counts = [[] for _ in handles]
+        shard.barrier()
+        tot_s16 = run_pair()
+        done_s16 = sum(len(c) for c in counts)
+        nsym_s16 = counts[0][0][1]
+        assert all(rc == 0 and ns == nsym_s16 for c in counts for rc, ns in c) and abs(nsym_s16 - nsym) <= 2, counts
+        e2e_s16_ms = tot_s16 / done_s16
+        del h_in16
         # device-resident, the same handles in flight together (input already in HBM, symbols left in HBM): what the
         # SMs deliver when the latency-bound certified re-run rounds of one step are filled by the kernels of another
         sym_devs = [sym_dev] + [torch.empty(2 * cap, dtype=torch.float32, device="cuda") for _ in extra]
@@ -416,6 +433,10 @@ def run_b200(args):
                 "note": "xrd_demod_batch on pinned host buffers; steps_in_flight = N: consecutive steps run on N demodulator "
                         "handles (N host threads), so the PCIe copies of one step overlap the kernels of the others; every "
                         "step's H2D and D2H are inside the timed region"},
+        "e2e_s16_in_i8_out": None if e2e_s16_ms is None else {
+            "value": n / e2e_s16_ms / 1e3, "unit": UNIT, "ms_per_step": e2e_s16_ms, "h2d_bytes_per_step": 4 * n,
+            "d2h_bytes_per_step": nsym, "steps_in_flight": in_flight, "scope": "rank 0",
+            "note": "xrd_demod_batch_i8 with XRD_S16IQ input: the reference's own ingest and egress formats"},
         "device_resident_in_flight": None if dev_conc_ms is None else {
             "value": n / dev_conc_ms / 1e3, "unit": UNIT, "ms_per_step": dev_conc_ms, "steps_in_flight": in_flight,
             "scope": "rank 0", "note": "xrd_demod_device on N handles together (wall clock, synchronised both sides); "
