@@ -128,11 +128,11 @@ fir1_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float
 #pragma unroll
         for (int q = 0; q < FIR_R; q++) {
             const float h = s_taps[kb + q];
+            const float2 h2 = make_float2(h, h);
 #pragma unroll
             for (int r = 0; r < FIR_R; r++) {
                 const int s = (r - q + FIR_R) % FIR_R;
-                acc[r].x = fmaf(h, w[s].x, acc[r].x);
-                acc[r].y = fmaf(h, w[s].y, acc[r].y);
+                acc[r] = __ffma2_rn(h2, w[s], acc[r]);   // two IEEE fmaf in one FFMA2 (I and Q share the tap)
             }
             // relative index -(k+1) enters the slot that (R-1-k) leaves
             w[(FIR_R - 1 - q) % FIR_R] = xb[-(kb + q) - 1];
@@ -142,11 +142,11 @@ fir1_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float
     for (int q = 0; q < FIR_R; q++) {
         if (kb + q < ntaps) {
             const float h = s_taps[kb + q];
+            const float2 h2 = make_float2(h, h);
 #pragma unroll
             for (int r = 0; r < FIR_R; r++) {
                 const int s = (r - q + FIR_R) % FIR_R;
-                acc[r].x = fmaf(h, w[s].x, acc[r].x);
-                acc[r].y = fmaf(h, w[s].y, acc[r].y);
+                acc[r] = __ffma2_rn(h2, w[s], acc[r]);   // two IEEE fmaf in one FFMA2 (I and Q share the tap)
             }
             w[(FIR_R - 1 - q) % FIR_R] = xb[-(kb + q) - 1];
         }
@@ -258,8 +258,7 @@ fird_poly_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const 
 #pragma unroll
                         for (int r = 0; r < R; r++) {
                             const int sl = (r - q + R) % R;
-                            acc[r].x = fmaf(h, w[p][sl].x, acc[r].x);
-                            acc[r].y = fmaf(h, w[p][sl].y, acc[r].y);
+                            acc[r] = __ffma2_rn(make_float2(h, h), w[p][sl], acc[r]);   // two IEEE fmaf in one FFMA2
                         }
                     }
                 }
