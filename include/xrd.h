@@ -38,6 +38,14 @@ typedef enum {
 #define XRD_FLOATIQ 0
 #define XRD_S16IQ 1
 #define XRD_S8IQ 2
+/* the two formats the reference's front ends convert themselves before the callback (accepted here so that a
+ * front end can hand over its raw buffer):
+ *   XRD_U8IQ    unsigned 8-bit, (v - 128) / 128.f          SpyServerFrontend.cpp:396-434 (:406)
+ *   XRD_RTLU8IQ RTL-SDR: lut[v] = (v - 128) / 127.f, then the one-pole DC blocker of RtlFrontend.cpp:104-116
+ *               (alpha from the sample rate, :57; its `i % 1` quirk -- one average for I and Q -- is kept).
+ *               The blocker is a serial filter with state: xrd_add_samples only. */
+#define XRD_U8IQ 3
+#define XRD_RTLU8IQ 4
 
 /* ---------------------------------------------------------------------------------------
  * Demodulator: replaces the globals + processSamples() of demodulator.cpp:31-52,100-168
@@ -81,14 +89,19 @@ typedef void (*xrd_symbols_cb)(void *user, int channel, const float *cf32_symbol
 /* == processSamples()   demodulator.cpp:100-168
  * Runs the chain on everything queued (if at least min_samples complex samples are queued per
  * channel; the reference's threshold is 32768, demodulator.cpp:113) and hands the symbols to
- * `cb`.  Returns the number of complex samples consumed per channel, 0 if below threshold. */
+ * `cb`.  Returns the number of complex samples consumed per channel, 0 if below threshold.
+ * With decimation > 1 the n % decimation trailing samples stay queued for the next call; the reference pops and
+ * drops them (demodulator.cpp:124-128,137), which shifts its decimation phase after every chunk whose length is not
+ * a multiple of the decimation -- a defect this path does not reproduce.
+ * On an error (< 0) nothing has been dequeued and `cb` has not run, but the loop state may have advanced:
+ * xrd_reset (or xrd_checkpoint_load) before feeding the same samples again. */
 int64_t xrd_process(xrd_demod *d, int64_t min_samples, xrd_symbols_cb cb, void *user);
 
 /* One-shot over HOST buffers (state carried across calls, like consecutive processSamples()
  * calls): iq holds n_channels blocks of n_complex samples of `type` (channel-major);
  * symbols (cf32) are written to sym_out[channel * cap ...], counts to n_sym[channel].
  * n_complex must be a multiple of the decimation (the reference silently drops the remainder,
- * demodulator.cpp:137; here it is an error). */
+ * demodulator.cpp:137; here it is an error).  `type`: XRD_FLOATIQ, XRD_S16IQ, XRD_S8IQ or XRD_U8IQ. */
 int xrd_demod_batch(xrd_demod *d, const void *iq, size_t n_complex, int type, float *sym_out, size_t cap,
                     int64_t *n_sym);
 
@@ -119,6 +132,23 @@ typedef struct {
     uint64_t n_in, n_sym;       /* totals since create / last set */
 } xrd_loop_state;
 int xrd_get_state(xrd_demod *d, int channel, xrd_loop_state *st);
+/* Puts the loop variables of one channel back (the reference's state lives in the five operator objects,
+ * demodulator.cpp:32-36).  Filter histories and the M&M sample tail are not part of xrd_loop_state: use the
+ * checkpoint calls below to continue a stream exactly. */
+int xrd_set_state(xrd_demod *d, int channel, const xrd_loop_state *st);
+
+/* Checkpoint / resume of the whole demodulator (all channels): loop variables, decimator and RRC histories,
+ * the M&M sample tail, totals.  A demodulator created with the same xrd_config that loads the blob continues the
+ * stream bit for bit where the saved one stopped (queued FIFO samples are input, not state, and are not saved).
+ * xrd_checkpoint_load returns XRD_E_STATE when the blob was saved under another configuration. */
+size_t xrd_checkpoint_size(const xrd_demod *d);
+int xrd_checkpoint_save(xrd_demod *d, void *blob, size_t cap);
+int xrd_checkpoint_load(xrd_demod *d, const void *blob, size_t bytes);
+
+/* Upper bound of the symbols one call over n_complex input samples per channel can produce (the capacity
+ * xrd_demod_batch / xrd_demod_device / xrd_demod_batch_i8 never overflow with); derived from omega, its
+ * relative limit and gain_mu exactly as the M&M stage sizes its own staging. */
+int64_t xrd_symbol_capacity(const xrd_demod *d, size_t n_complex);
 
 /* Back to the just-created state (loop states, filter histories, queued samples, totals):
  * what deleting and re-constructing the five operators does in the reference
@@ -129,22 +159,25 @@ int xrd_reset(xrd_demod *d);
  * time with CUDA events or order their own device work against it). */
 void *xrd_stream(xrd_demod *d);
 
-/* Segmentation of the time-parallel loops (samples); 0 keeps the default.  Results do not
- * depend on these values -- hand-offs are certified bitwise -- only speed does. */
+/* Segmentation and kernel choice of the time-parallel loops; 0 keeps the default everywhere.
+ * Results do not depend on these values -- hand-offs are certified bitwise -- only speed does
+ * (tests force small segments and every kernel shape through this). */
 typedef struct {
-    int32_t agc_seg, agc_warm;
-    int32_t costas_seg, costas_warm;
-    int64_t mm_seg, mm_warm;
-    int32_t mm_lanes;            /* M&M chain kernel (tests/tuning): 0 default (mm_chain32_kernel, 1024 lanes); 128/256/512/1024 =
-                                    mm_chain32_kernel with that many lanes (+0x10000: the generic 64-bit kernel);
-                                    0x20000 + (slots per thread << 8) + warps = window-Newton chain of that shape;
-                                    + 0x40000: certified re-runs with the chain kernel instead of the relative walk
-                                    (mm_delta_kernel); + (1|2|3) << 20: 128|256|512 lanes for that walk (default 512) */
-    int32_t loop_kernel;         /* AGC/Costas kernel: 0 default, 1 one thread per segment, 2 window-Newton warp chains,
-                                    3..6 window-Newton CTA chains with (slots per thread, warps) = (1,4) (2,4) (1,2) (2,2) */
-    int32_t h2d_pieces;          /* host-input calls: copy/compute pieces (low byte; 0 default = up to 2, 1 = one copy) and,
-                                    above it, the minimum piece in Ki samples (0 default = 16 M samples) */
-    int32_t reserved;            /* tuning experiments: chains per SM, Costas | AGC << 8 (0 keeps defaults) */
+    int32_t agc_seg, agc_warm;         /* AGC segment / speculative warm-up (samples) */
+    int32_t costas_seg, costas_warm;   /* Costas segment / warm-up (samples) */
+    int64_t mm_seg, mm_warm;           /* M&M segment / warm-up (samples) */
+    int32_t mm_lanes;                  /* lanes of the M&M chain kernel: 128, 256, 512 or 1024 (default) */
+    int32_t mm_kernel;                 /* 1: 32-bit fixed-point chain kernel where valid (default); 2: generic 64-bit kernel */
+    int32_t mm_rerun;                  /* certified M&M re-runs: 1 walk relative to the recorded trajectory (default),
+                                          2 chain-kernel re-runs */
+    int32_t mm_walk_lanes;             /* lanes of that walk: 128, 256 or 512 (default) */
+    int32_t loop_kernel;               /* AGC/Costas first pass: 1 one thread per segment, 2 window-Newton warp chains
+                                          (default), 3..7 window-Newton CTA chains with (slots per thread, warps) =
+                                          (1,4) (2,4) (1,2) (2,2) (2,8) */
+    int32_t rerun_kernel;              /* AGC/Costas certified re-runs: 2..7 as above (default 4) */
+    int32_t h2d_pieces;                /* host-input calls: copy/compute pieces, 1..16 (default 2) */
+    int32_t h2d_piece_min_ki;          /* minimum piece, Ki samples (default 16 M samples) */
+    int32_t costas_chains_per_sm, agc_chains_per_sm;   /* segments per SM of the first pass (defaults 8, 16) */
 } xrd_tuning;
 int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t);
 

@@ -15,7 +15,8 @@
 // as one object with the reference's two seams -- addSamples(void*, int, int) is
 // onSamplesAvailable (demodulator.cpp:54-74, the callback type of
 // FrontendDevice::SetSamplesAvailableCallback, FrontendDevice.h:37) and the sink is anything with
-// add(std::complex<float>*, int) (SymbolManager.h:37).
+// add(std::complex<float>*, int) (SymbolManager.h:37); an optional second sink with
+// addSamples(const float*, int) receives what DiagManager::addSamples does (demodulator.cpp:161-163).
 //
 // Every Work() runs hand-written sm_100a kernels through libxrd.so; errors surface as
 // SatHelperException exactly where the reference catches them.  There is no CPU path here.
@@ -26,6 +27,7 @@
 #include <cstdint>
 #include <exception>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -181,12 +183,22 @@ public:
     // Returns the number of complex samples consumed.
     template <class Sink> int64_t processSamples(Sink &sink, int64_t minSamples = 32768)
     {
+        NoDiag none;
+        return processSamples(sink, none, minSamples);
+    }
+    // The same with the reference's diagnostic tap (demodulator.cpp:161-163): after sink.add(ba, symbols),
+    // diag.addSamples((float *)ba, symbols < 1024 ? symbols : 1024) -- DiagManager::addSamples (DiagManager.h:35)
+    // sees the first min(symbols, 1024) FLOATS of the interleaved complex symbol buffer of every chunk.
+    template <class Sink, class Diag> int64_t processSamples(Sink &sink, Diag &diag, int64_t minSamples = 32768)
+    {
         open();
-        struct Ctx { Sink *s; } ctx{&sink};
+        struct Ctx { Sink *s; Diag *g; } ctx{&sink, &diag};
         const int64_t rc = xrd_process(
             h, minSamples,
             [](void *user, int /*channel*/, const float *sym, int n) {
-                static_cast<Ctx *>(user)->s->add(reinterpret_cast<std::complex<float> *>(const_cast<float *>(sym)), n);
+                Ctx *c = static_cast<Ctx *>(user);
+                c->s->add(reinterpret_cast<std::complex<float> *>(const_cast<float *>(sym)), n);
+                c->g->addSamples(sym, n < 1024 ? n : 1024);
             },
             &ctx);
         if (rc < 0) throw SatHelper::SatHelperException(xrd_last_error(h));
@@ -224,6 +236,24 @@ public:
         if (xrd_get_state(h, channel, &st) < 0) throw SatHelper::SatHelperException(xrd_last_error(h));
         return st;
     }
+    void setState(const xrd_loop_state &st, int channel = 0)
+    {
+        open();
+        if (xrd_set_state(h, channel, &st) < 0) throw SatHelper::SatHelperException(xrd_last_error(h));
+    }
+    // checkpoint / resume of the whole demodulator (loop variables, filter histories, M&M tail, totals)
+    std::vector<unsigned char> checkpoint()
+    {
+        open();
+        std::vector<unsigned char> blob(xrd_checkpoint_size(h));
+        if (xrd_checkpoint_save(h, blob.data(), blob.size()) < 0) throw SatHelper::SatHelperException(xrd_last_error(h));
+        return blob;
+    }
+    void restore(const std::vector<unsigned char> &blob)
+    {
+        open();
+        if (xrd_checkpoint_load(h, blob.data(), blob.size()) < 0) throw SatHelper::SatHelperException(xrd_last_error(h));
+    }
     const char *lastError() const { return xrd_last_error(h); }
     xrd_demod *handle()
     {
@@ -231,14 +261,25 @@ public:
         return h;
     }
 
-private:
-    xrd_config cfg;
-    xrd_demod *h = nullptr;
+    // Creates the device side now instead of on first use.  The reference wires addSamples to the frontend
+    // thread and processSamples to the symbol-loop thread (demodulator.cpp:434,475); the first calls of the two
+    // may race, so creation is serialised (std::call_once) whichever thread gets there first.
     void open()
     {
-        if (h) return;
-        if (xrd_create(&cfg, &h) != XRD_OK) throw SatHelper::SatHelperException(xrd_last_error(nullptr));
+        std::call_once(once, [this]() {
+            if (xrd_create(&cfg, &h) != XRD_OK) createError = xrd_last_error(nullptr);
+        });
+        if (!h) throw SatHelper::SatHelperException(createError.empty() ? "xrd_create failed" : createError);
     }
+
+private:
+    struct NoDiag {
+        void addSamples(const float *, int) {}
+    };
+    xrd_config cfg;
+    xrd_demod *h = nullptr;
+    std::once_flag once;
+    std::string createError;
 };
 
 }  // namespace xrd

@@ -258,6 +258,28 @@ void xo_fir_free(xo_fir *f)
     free(f);
 }
 
+/*
+ * Alternative summation order for cross-checks only (xo_set_fir_simd(1)): libSatHelper's FirFilter
+ * evaluates the tap sum with a SIMD dot product, whose order is not the serial one.  This restates
+ * the common 4-lane form -- lane l accumulates taps l, l+4, l+8, ... with separate multiply and add
+ * (no FMA), the four lanes are added pairwise at the end -- so that tests can measure how far a
+ * different but equally valid order moves the chain output (tests/test_oracle.py).
+ */
+static int xo_fir_simd = 0;
+void xo_set_fir_simd(int on) { xo_fir_simd = on; }
+
+static void xo_fir_dot_simd(const float *taps, int T, const float *x /* x[-2k] = sample k back */, float *o)
+{
+    float ar[4] = {0, 0, 0, 0}, ai[4] = {0, 0, 0, 0};
+    for (int k = 0; k < T; k++) {
+        const float pr = taps[k] * x[-2 * k], pi = taps[k] * x[-2 * k + 1];
+        ar[k & 3] = ar[k & 3] + pr;
+        ai[k & 3] = ai[k & 3] + pi;
+    }
+    o[0] = (ar[0] + ar[1]) + (ar[2] + ar[3]);
+    o[1] = (ai[0] + ai[1]) + (ai[2] + ai[3]);
+}
+
 /* out[i] = sum_{k=0}^{T-1} taps[k] * x[i*D - k], accumulated k = 0..T-1 with fmaf. */
 void xo_fir_work(xo_fir *f, const float *in, float *out, int n_out)
 {
@@ -275,7 +297,10 @@ void xo_fir_work(xo_fir *f, const float *in, float *out, int n_out)
     memcpy(w, f->hist, sizeof(float) * 2 * (size_t)H);
     memcpy(w + 2 * (size_t)H, in, sizeof(float) * 2 * n_in);
     const float *taps = f->taps;
-    if (D == 1) {
+    if (xo_fir_simd) {
+        for (size_t i = 0; i < (size_t)n_out; i++)
+            xo_fir_dot_simd(taps, T, w + 2 * (i * D + (size_t)H), out + 2 * i);
+    } else if (D == 1) {
         enum { BLK = 64 };
         size_t i = 0;
         for (; i + BLK <= (size_t)n_out; i += BLK) {
@@ -749,4 +774,27 @@ void xo_convert_s8(const int8_t *in, int64_t n_complex, float *out)
 {
     for (int64_t i = 0; i < 2 * n_complex; i++)
         out[i] = in[i] / 128.f;
+}
+
+/* SpyServer u8 samples (SpyServerFrontend.cpp:404-407): (v - 128) / 128.f */
+void xo_convert_u8(const uint8_t *in, int64_t n_complex, float *out)
+{
+    for (int64_t i = 0; i < 2 * n_complex; i++)
+        out[i] = (in[i] - 128) / 128.f;
+}
+
+/* RtlFrontend (RtlFrontend.cpp:27,57,104-116): lut[v] = (v - 128) * (1.f / 127.f), then the DC
+ * blocker.  The reference tests `i % 1` (always 0), so every float -- I and Q -- goes through the
+ * one running average iavg; kept as is.  *avg carries the state across calls. */
+float xo_rtl_alpha(uint32_t sample_rate) { return (float)(1.f - exp(-1.0 / (sample_rate * 0.05f))); }
+void xo_convert_rtl_u8(const uint8_t *in, int64_t n_complex, float alpha, float *avg, float *out)
+{
+    float iavg = *avg;
+    for (int64_t i = 0; i < 2 * n_complex; i++) {
+        float v = (in[i] - 128) * (1.f / 127.f);
+        iavg += alpha * (v - iavg);
+        v -= iavg;
+        out[i] = v;
+    }
+    *avg = iavg;
 }

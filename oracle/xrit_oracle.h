@@ -48,6 +48,8 @@ void xo_costas_gains(float loop_bw, float *alpha, float *beta);
 void xo_sincosf(float x, float *sn, float *cs);
 void xo_sincosf_array(const float *x, int64_t n, float *sn, float *cs);
 void xo_set_libm_sincos(int on);
+/* cross-check only: FIR tap sums in a 4-lane SIMD order without FMA instead of the serial fmaf order */
+void xo_set_fir_simd(int on);
 
 /* ---- stage operators: SatHelper::{FirFilter,AGC,CostasLoop,ClockRecovery} ---- */
 typedef struct xo_fir xo_fir;
@@ -117,6 +119,10 @@ void xo_soft_i8(const float *sym_cf32, int64_t n, int8_t *out);
 /* onSamplesAvailable conversions (demodulator.cpp:57-70) */
 void xo_convert_s16(const int16_t *in, int64_t n_complex, float *out);
 void xo_convert_s8(const int8_t *in, int64_t n_complex, float *out);
+/* the u8 formats two front ends convert themselves: SpyServerFrontend.cpp:404-407, RtlFrontend.cpp:27,57,104-116 */
+void xo_convert_u8(const uint8_t *in, int64_t n_complex, float *out);
+float xo_rtl_alpha(uint32_t sample_rate);
+void xo_convert_rtl_u8(const uint8_t *in, int64_t n_complex, float alpha, float *avg, float *out);
 
 #ifdef __cplusplus
 }

@@ -116,6 +116,11 @@ def lib():
     L.xo_soft_i8.argtypes = [vp, C.c_int64, vp]
     L.xo_convert_s16.argtypes = [vp, C.c_int64, vp]
     L.xo_convert_s8.argtypes = [vp, C.c_int64, vp]
+    L.xo_convert_u8.argtypes = [vp, C.c_int64, vp]
+    L.xo_rtl_alpha.argtypes = [C.c_uint32]
+    L.xo_rtl_alpha.restype = C.c_float
+    L.xo_convert_rtl_u8.argtypes = [vp, C.c_int64, C.c_float, fp, vp]
+    L.xo_set_fir_simd.argtypes = [C.c_int]
     _LIB = L
     return L
 
@@ -314,3 +319,24 @@ def convert_s8(x):
     out = np.empty(len(x), np.float32)
     lib().xo_convert_s8(_p(x), len(x) // 2, _p(out))
     return out.view(np.complex64)
+
+
+def convert_u8(x):
+    x = np.ascontiguousarray(x, np.uint8).reshape(-1)
+    out = np.empty(len(x), np.float32)
+    lib().xo_convert_u8(_p(x), len(x) // 2, _p(out))
+    return out.view(np.complex64)
+
+
+class RtlU8:
+    """RtlFrontend's u8 conversion with its DC blocker; state carried across calls"""
+
+    def __init__(self, sample_rate):
+        self.alpha = lib().xo_rtl_alpha(sample_rate)
+        self.avg = C.c_float(0.0)
+
+    def convert(self, x):
+        x = np.ascontiguousarray(x, np.uint8).reshape(-1)
+        out = np.empty(len(x), np.float32)
+        lib().xo_convert_rtl_u8(_p(x), len(x) // 2, self.alpha, C.byref(self.avg), _p(out))
+        return out.view(np.complex64)

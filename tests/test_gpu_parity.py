@@ -65,8 +65,9 @@ def test_fir_tap_sweep(gpu, xrd, oracle, stages, ntaps):
     assert_bitexact(xrd.FirFilter(1, taps).Work(x), oracle.Fir(1, taps).work(x), "fir %d taps" % ntaps)
 
 
-@pytest.mark.parametrize("decim", [2, 4, 5])
+@pytest.mark.parametrize("decim", [2, 3, 4, 5, 6, 8])
 def test_decimating_fir(gpu, xrd, oracle, decim):
+    """polyphase kernels for decimation 2..5, the generic kernel from 6 up"""
     _, x = make_signal("hrit10", 400000)
     taps = xrd.lowpass_taps(1, 10e6, 10e6 / decim / 2, 100e3)
     assert len(taps) == 241
@@ -146,37 +147,37 @@ def test_costas_branch_resolution_over_carrier_offsets(gpu, xrd, oracle, df_hz, 
     assert_bitexact(c.Work(taps["rrc"]), taps["costas"], "Costas, df %g Hz" % df_hz)
 
 
-@pytest.mark.parametrize("lanes", [256, 1024, 0x10000 + 256, 0x20000 + (2 << 8) + 16, 0x20000 + (4 << 8) + 8, 0x20000 + (1 << 8) + 16])
+@pytest.mark.parametrize("lanes,kernel", [(128, 1), (256, 1), (512, 1), (1024, 1), (256, 2)])
 @pytest.mark.parametrize("mode", ["hrit", "lrit"])
-def test_mm_chain_kernels_agree(gpu, xrd, oracle, mode, lanes):
-    """every M&M chain kernel (32-bit fixed point, generic 64-bit, window-Newton shapes) gives the oracle's symbols,
-    with segments short enough to need certified re-runs"""
+def test_mm_chain_kernels_agree(gpu, xrd, oracle, mode, lanes, kernel):
+    """every shape of the M&M chain kernel (32-bit fixed point with 128..1024 lanes, the generic 64-bit kernel)
+    gives the oracle's symbols, with segments short enough to need certified re-runs"""
     _, x = make_signal(mode, 1 << 21)
     ref = oracle.Chain(oracle.config(mode == "hrit")).process(x)
     d = xrd.Demodulator(mode=mode)
-    d.set_tuning(mm_lanes=lanes, mm_seg=150000, mm_warm=60000)
+    d.set_tuning(mm_lanes=lanes, mm_kernel=kernel, mm_seg=150000, mm_warm=60000)
     half = len(x) // 2 + 12345
     got = np.concatenate([d.demod(x[:half]), d.demod(x[half:])])
-    check_symbols(got, ref, "M&M kernel %#x" % lanes)
+    check_symbols(got, ref, "M&M kernel %d lanes, kind %d" % (lanes, kernel))
     assert d.stats()["mm_redo"] > 0
 
 
 @pytest.mark.parametrize("warm", [60000, 20000, 1500])
-@pytest.mark.parametrize("lanes", [0, 1 << 20, 2 << 20, 0x40000])
-def test_mm_relative_reruns(gpu, xrd, oracle, lanes, warm):
+@pytest.mark.parametrize("walk_lanes,rerun", [(0, 0), (128, 1), (256, 1), (0, 2)])
+def test_mm_relative_reruns(gpu, xrd, oracle, walk_lanes, rerun, warm):
     """certified M&M re-runs as a walk relative to the trajectory in place (mm_delta_kernel: 512, 128 and 256 lanes) and
-    with the chain kernel (0x40000) give the oracle's symbols; a warm-up too short to land near the true trajectory
+    with the chain kernel (mm_rerun=2) give the oracle's symbols; a warm-up too short to land near the true trajectory
     makes the walk give up and fall back to the chain kernel"""
     _, x = make_signal("hrit", 1 << 21)
     ref = oracle.Chain(oracle.config(True)).process(x)
     d = xrd.Demodulator(mode="hrit")
-    d.set_tuning(mm_lanes=lanes, mm_seg=100000, mm_warm=warm)
+    d.set_tuning(mm_walk_lanes=walk_lanes, mm_rerun=rerun, mm_seg=100000, mm_warm=warm)
     third = len(x) // 3 + 777
     got = np.concatenate([d.demod(x[:third]), d.demod(x[third:2 * third]), d.demod(x[2 * third:])])
-    check_symbols(got, ref, "M&M re-runs %#x, warm-up %d" % (lanes, warm))
+    check_symbols(got, ref, "M&M re-runs (walk lanes %d, rerun %d), warm-up %d" % (walk_lanes, rerun, warm))
     st = d.stats()
     assert st["mm_redo"] > 0
-    if lanes & 0x40000:
+    if rerun == 2:
         assert st["mm_bail"] == 0
 
 
@@ -208,7 +209,7 @@ def test_host_calls_in_pieces(gpu, xrd, oracle, pieces):
     _, x = make_signal("hrit", 1 << 21)
     ref = oracle.Chain(oracle.config(True)).process(x)
     d = xrd.Demodulator(mode="hrit")
-    d.set_tuning(h2d_pieces=pieces | (100 << 8))     # pieces of >= 100 Ki samples
+    d.set_tuning(h2d_pieces=pieces, h2d_piece_min_ki=100)     # pieces of >= 100 Ki samples
     cut = 1_200_003
     got = np.concatenate([d.demod(x[:cut]), d.demod(x[cut:])])
     check_symbols(got, ref, "%d pieces" % pieces)
@@ -237,6 +238,15 @@ def test_chain_fifo_seam(gpu, xrd, oracle):
     import ctypes as C
     raw = np.ascontiguousarray(x[:10]).view(np.float32)
     assert xrd.lib().xrd_add_samples(d._h, 0, raw.ctypes.data_as(C.c_void_p), 10, 7) == -1   # unknown sample type
+    # a failed call leaves the queue alone and a full queue drains in order (ring wrap-around)
+    d2, ch2, got2 = xrd.Demodulator(mode="lrit"), oracle.Chain(oracle.config(False)), []
+    pos = 0
+    for k in (65535, 65535, 65535, 400000, 7, 65535, 333333, 65535):
+        d2.add_samples(x[pos:pos + k])
+        pos += k
+        d2.process(lambda ch, s: got2.append(s), min_samples=100000)
+    d2.process(lambda ch, s: got2.append(s), min_samples=1)
+    check_symbols(np.concatenate(got2), ch2.process(x[:pos]), "FIFO seam, ring wrap-around")
 
 
 @pytest.mark.parametrize("ntaps", [15, 31, 63, 127, 255])
@@ -300,6 +310,118 @@ def test_noise_free_and_extreme_inputs(gpu, xrd, oracle):
     rng = np.random.default_rng(5)         # pure noise: loops never lock, speculation must still be repaired
     w = (0.2 * (rng.standard_normal(300000) + 1j * rng.standard_normal(300000))).astype(np.complex64)
     check_symbols(xrd.Demodulator(mode="hrit").demod(w), oracle.Chain(oracle.config(True)).process(w), "noise only")
+
+
+@pytest.mark.parametrize("decim", [3, 6])
+def test_chain_other_decimations(gpu, xrd, oracle, decim):
+    """the chain with decimation 3 (polyphase kernel) and 6 (generic decimating kernel), two ragged calls"""
+    from xritdemod_b200 import siggen as sg
+
+    fs = 2500000 * decim
+    p = sg.params("hrit", 0, n=1 << 20, ramp_len=1 << 20)
+    p.sample_rate = float(fs)                  # HRIT at decim x 2.5 Msps: 2.5 Msps after the decimator
+    x = sg.generate(p, 1 << 20)
+    kw = dict(sample_rate=fs, decimation=decim)
+    ref = oracle.Chain(oracle.config(True, **kw)).process(x[: (len(x) // decim) * decim])
+    d = xrd.Demodulator(mode="hrit", **kw)
+    cut = (len(x) // 3 // decim) * decim
+    end = (len(x) // decim) * decim
+    got = np.concatenate([d.demod(x[:cut]), d.demod(x[cut:end])])
+    check_symbols(got, ref, "chain, decimation %d" % decim)
+
+
+def test_non_finite_samples_terminate(gpu, xrd):
+    """a NaN (or an Inf followed by a zero) makes the AGC gain NaN for good -- in the reference too, which then
+    spins in its timing loop; here every stage must still terminate: the loops propagate the NaN (hand-offs are
+    certified bitwise, so a NaN state equals itself) and the call returns an error or NaN symbols, never hangs"""
+    _, x = make_signal("hrit", 600000)
+    for bad in (np.nan, np.inf):
+        y = x.copy()
+        y[300000] = bad
+        y[300001] = 0
+        d = xrd.Demodulator(mode="hrit")
+        try:
+            sym = d.demod(y)
+            assert not np.isfinite(sym[-1000:]).all()
+        except xrd.XrdError as e:
+            assert e.code == -4      # the timing loop stopped advancing: reported as overflow
+        d.reset()
+        check = d.demod(x[:100000])  # the handle is usable again after a reset
+        assert np.isfinite(check).all() and len(check) > 30000
+    a = xrd.AGC()
+    y = x[:200000].copy()
+    y[1000] = np.nan
+    out = a.Work(y)
+    assert np.isfinite(out[:1000]).all() and np.isnan(out[-1].real)
+    c = xrd.CostasLoop()
+    out = c.Work(y)
+    assert np.isfinite(out[:1000]).all() and np.isnan(out[-1].real)
+
+
+@pytest.mark.parametrize("nch", [1, 3])
+def test_checkpoint_resume_and_set_state(gpu, xrd, oracle, nch):
+    """run A then B on one demodulator; checkpoint after A, restore into a NEW demodulator and run B there: the
+    symbols equal the tail of the uninterrupted run (loop variables, RRC/decimator histories, M&M tail, totals);
+    xrd_set_state alone puts the loop variables back"""
+    kw = dict(sample_rate=10000000, decimation=4) if nch == 1 else {}
+    n = 1 << 20
+    xs = np.stack([make_signal("hrit10" if nch == 1 else "hrit", n, channel=c)[1] for c in range(nch)])
+    cut = 400000
+    d = xrd.Demodulator(mode="hrit", n_channels=nch, **kw)
+    fresh = xrd.Demodulator(mode="hrit", n_channels=nch, **kw)
+    blob0 = fresh.checkpoint()                       # before any call: histories are zero
+    a = d.demod(xs[:, :cut] if nch > 1 else xs[0, :cut])
+    blob = d.checkpoint()
+    assert len(blob) == xrd.lib().xrd_checkpoint_size(d._h) and blob != blob0
+    b = d.demod(xs[:, cut:] if nch > 1 else xs[0, cut:])
+    d2 = xrd.Demodulator(mode="hrit", n_channels=nch, **kw)
+    d2.restore(blob)
+    b2 = d2.demod(xs[:, cut:] if nch > 1 else xs[0, cut:])
+    for c in range(nch):
+        ref = oracle.Chain(oracle.config(True, **kw)).process(xs[c])
+        ga, gb, gb2 = (a, b, b2) if nch == 1 else (a[c], b[c], b2[c])
+        check_symbols(np.concatenate([ga, gb]), ref, "uninterrupted, channel %d" % c)
+        assert_bitexact(gb2, gb, "resumed from the checkpoint, channel %d" % c)
+        s1, s2 = d.state(c), d2.state(c)
+        assert (s1.n_in, s1.n_sym, s1.mm_mu, s1.agc_gain) == (s2.n_in, s2.n_sym, s2.mm_mu, s2.agc_gain)
+    d3 = xrd.Demodulator(mode="lrit", n_channels=nch)
+    with pytest.raises(xrd.XrdError) as e:
+        d3.restore(blob)                              # another configuration
+    assert e.value.code == -5
+    # set_state: the loop variables of channel 0 only
+    st = d.state(0)
+    d2.reset()
+    d2.set_state(st, 0)
+    got = d2.state(0)
+    for f in ("agc_gain", "costas_phase", "costas_freq", "mm_mu", "mm_omega", "mm_next", "n_in", "n_sym"):
+        assert getattr(got, f) == getattr(st, f), f
+    assert list(got.mm_p0) == list(st.mm_p0) and list(got.mm_p1) == list(st.mm_p1)
+
+
+def test_u8_ingest_formats(gpu, xrd, oracle, siggen):
+    """XRD_U8IQ (SpyServerFrontend.cpp:406) through the device path and the FIFO seam; XRD_RTLU8IQ (RtlFrontend.cpp:
+    104-116, LUT + DC blocker with state across callbacks) through the FIFO seam"""
+    _, x = make_signal("hrit", 1 << 19, amp=(0.3, 0.6))
+    raw = siggen.to_u8(x)
+    ref = oracle.Chain(oracle.config(True)).process(oracle.convert_u8(raw))
+    check_symbols(xrd.Demodulator(mode="hrit").demod(raw, type=xrd.XRD_U8IQ), ref, "u8 device path")
+    d = xrd.Demodulator(mode="hrit")
+    got = []
+    for pos in range(0, len(raw), 2 * 65535):
+        d.add_samples(raw[pos:pos + 2 * 65535], type=xrd.XRD_U8IQ)
+        d.process(lambda ch, s: got.append(s), min_samples=1)
+    check_symbols(np.concatenate(got), ref, "u8 via add_samples")
+    conv = oracle.RtlU8(2500000)
+    xf = np.concatenate([conv.convert(raw[pos:pos + 2 * 65535]) for pos in range(0, len(raw), 2 * 65535)])
+    ref = oracle.Chain(oracle.config(True)).process(xf)
+    d = xrd.Demodulator(mode="hrit")
+    got = []
+    for pos in range(0, len(raw), 2 * 65535):
+        d.add_samples(raw[pos:pos + 2 * 65535], type=xrd.XRD_RTLU8IQ)
+        d.process(lambda ch, s: got.append(s), min_samples=1)
+    check_symbols(np.concatenate(got), ref, "RTL u8 via add_samples")
+    with pytest.raises(xrd.XrdError):
+        xrd.Demodulator(mode="hrit").demod(raw, type=xrd.XRD_RTLU8IQ)   # serial DC blocker: FIFO seam only
 
 
 def test_reset_and_state(gpu, xrd, oracle):

@@ -281,3 +281,58 @@ def test_golden_fixture(oracle):
         assert_bitexact(sym[:256], g[mode + "_sym_head"], mode + " golden head")
         assert_bitexact(sym[-256:], g[mode + "_sym_tail"], mode + " golden tail")
         assert np.float64(sym.real.astype(np.float64).sum()) == g[mode + "_resum"]
+
+
+# ---------------------------------------------------------------------------- distance to other valid builds
+def _chain_stats(oracle, n, setter):
+    """soft symbols of the default oracle against the oracle with one arithmetic detail swapped"""
+    _, x = make_signal("hrit", n)
+    ref = oracle.Chain(oracle.config(True)).process(x)
+    setter(1)
+    try:
+        alt = oracle.Chain(oracle.config(True)).process(x)
+    finally:
+        setter(0)
+    assert abs(len(alt) - len(ref)) <= 1
+    m = min(len(alt), len(ref))
+    d = alt[:m].real.astype(np.float64) - ref[:m].real
+    return float(np.sqrt(np.mean(d * d))), float(np.abs(d).max()), float(np.mean(np.abs(d) > 5e-4)), m
+
+
+def test_distance_to_a_libm_sincos_build(oracle):
+    """The oracle's Costas NCO is a fully specified FP32 routine; libSatHelper calls libm.  This measures, at chain
+    level, how far that one substitution moves the soft symbols: the honest distance between "bit-exact against the
+    oracle" and "against a libm build of the reference" (parity is unpinned).  The two NCOs differ by
+    <= 2 ulp per call; M&M's rint(mu * 128) row choice turns that into isolated ~1e-3 steps."""
+    rms, mx, frac, m = _chain_stats(oracle, 1 << 22, oracle.lib().xo_set_libm_sincos)
+    print("libm sincos vs specified sincos: rms %.3g max %.3g fraction(|d| > 5e-4) %.3g over %d symbols" % (rms, mx, frac, m))
+    assert rms < 1.5e-3 and mx < 2e-2 and frac < 0.25
+
+
+def test_distance_to_a_simd_summation_order_fir(oracle):
+    """the same for the FIR tap sum: libSatHelper's dot product is SIMD (4 partial sums, no FMA), the oracle's is the
+    serial fmaf order; both are valid evaluations of FirFilter::Work"""
+    rms, mx, frac, m = _chain_stats(oracle, 1 << 22, oracle.lib().xo_set_fir_simd)
+    print("SIMD-order FIR vs serial fmaf FIR: rms %.3g max %.3g fraction(|d| > 5e-4) %.3g over %d symbols" % (rms, mx, frac, m))
+    assert rms < 1.5e-3 and mx < 2e-2 and frac < 0.25
+
+
+def test_u8_conversions(oracle):
+    """SpyServer u8 (SpyServerFrontend.cpp:406) and RTL u8 with its DC blocker (RtlFrontend.cpp:27,57,104-116)"""
+    raw = np.arange(256, dtype=np.uint8)
+    got = oracle.convert_u8(raw).view(np.float32)
+    np.testing.assert_array_equal(got, ((raw.astype(np.int32) - 128) / np.float32(128.0)).astype(np.float32))
+    rng = np.random.default_rng(3)
+    raw = rng.integers(0, 256, 20000, dtype=np.uint8)
+    r = oracle.RtlU8(2560000)
+    a = np.concatenate([r.convert(raw[:7000]), r.convert(raw[7000:])]).view(np.float32)
+    # alpha = 1.f - exp(-1.0 / (sampleRate * 0.05f)): the product is float, everything after it double (RtlFrontend.cpp:57)
+    alpha = np.float32(1.0 - np.exp(-1.0 / float(np.float32(2560000) * np.float32(0.05))))
+    assert r.alpha == alpha
+    avg = np.float32(0)
+    exp = np.empty(len(raw), np.float32)
+    for i, v in enumerate(raw):                       # every float through ONE average (`i % 1` in the reference)
+        f = np.float32(int(v) - 128) * (np.float32(1.0) / np.float32(127.0))
+        avg = np.float32(avg + np.float32(alpha * np.float32(f - avg)))
+        exp[i] = np.float32(f - avg)
+    np.testing.assert_array_equal(a, exp)

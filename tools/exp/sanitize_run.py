@@ -6,8 +6,9 @@ import numpy as np
 from xritdemod_b200 import demod as xd, siggen
 N = 400000
 x = siggen.generate(siggen.params("hrit", 0, n=N, ramp_len=N), N)
-CASES = (dict(), dict(loop_kernel=4), dict(loop_kernel=1), dict(mm_lanes=0x20000 + (2 << 8) + 16), dict(mm_lanes=256),
-           dict(mm_lanes=(1 << 20) + 256), dict(mm_lanes=(2 << 20)), dict(mm_lanes=0x40000 + 512), dict(mm_warm=2000))
+CASES = (dict(), dict(loop_kernel=4), dict(loop_kernel=1), dict(mm_lanes=256),
+           dict(mm_lanes=256, mm_walk_lanes=128), dict(mm_walk_lanes=256), dict(mm_lanes=512, mm_rerun=2), dict(mm_kernel=2, mm_lanes=256),
+           dict(mm_warm=2000))
 for kw in CASES[int(os.environ.get("FIRST_CASE", "0")):]:
     d = xd.Demodulator(mode="hrit")
     t = dict(costas_seg=16384, costas_warm=4096, agc_seg=8192, agc_warm=1024, mm_seg=60000, mm_warm=30000)

@@ -6,8 +6,12 @@
 // proves those call shapes compile and run against the B200 path; run_demodulator() drives the same
 // stream through xrd::Demodulator's two seams (sample callback in, SymbolManager-style sink out).
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <complex>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -32,6 +36,12 @@ const float AGC_RATE = 0.01f, AGC_REFERENCE = 0.5f, AGC_GAIN = 1.f, AGC_MAX_GAIN
 struct CollectingSink {
     std::vector<std::complex<float>> symbols;
     void add(std::complex<float> *data, int length) { symbols.insert(symbols.end(), data, data + length); }
+};
+
+// stands in for DiagManager (DiagManager.h:35, DiagManager.cpp:60-64): collects what addSamples() is given
+struct CollectingDiag {
+    std::vector<float> floats;
+    void addSamples(const float *data, int length) { floats.insert(floats.end(), data, data + length); }
 };
 
 inline void swapBuffers(std::complex<float> **a, std::complex<float> **b) { std::swap(*a, *b); }
@@ -118,6 +128,85 @@ long long shim_run_demodulator(const void *raw, long long n, int type, int hrit,
             return -1;
         }
         memcpy(symOut, symbolManager.symbols.data(), sizeof(float) * 2 * (size_t)ns);
+        return ns;
+    } catch (SatHelperException &e) {
+        g_error = e.reason();
+        return -1;
+    }
+}
+
+// The reference's thread wiring (demodulator.cpp:434,472-475): the frontend thread fires the sample callback, the
+// symbol-loop thread polls processSamples(); the first calls of the two race to create the device side.  A
+// DiagManager-style tap runs beside the sink (demodulator.cpp:161-163).  With threads == 0 the two alternate on
+// the calling thread, one processSamples() per callback, which makes the taps deterministic.  Half way through,
+// the demodulator is checkpointed and a NEW demodulator restored from the blob carries on (threads == 0 only).
+long long shim_run_wired(const void *raw, long long n, int type, int hrit, int block, int threads, int checkpoint_at_block,
+                         float *symOut, long long cap, float *diagOut, long long diagCap, long long *nDiag)
+{
+    try {
+        std::unique_ptr<xrd::Demodulator> demod(new xrd::Demodulator(hrit != 0));
+        CollectingSink symbolManager;
+        CollectingDiag diagManager;
+        const size_t bytes = (type == XRD_FLOATIQ) ? 8 : (type == XRD_S16IQ ? 4 : 2);
+        if (threads) {
+            std::atomic<bool> produced{false};
+            std::string producerError;
+            std::thread frontend([&]() {
+                try {
+                    xrd::Demodulator::SamplesCallback cb = demod->callback();
+                    for (long long pos = 0; pos < n; pos += block) {
+                        const int length = (int)std::min<long long>(block, n - pos);
+                        // a real frontend drops on overflow (demodulator.cpp:104-106); the test waits instead
+                        while (!demod->addSamples((void *)((const char *)raw + bytes * (size_t)pos), length, type))
+                            std::this_thread::sleep_for(std::chrono::microseconds(200));
+                    }
+                } catch (SatHelperException &e) {
+                    producerError = e.reason();
+                }
+                produced = true;
+            });
+            std::string loopError;
+            std::thread symbolThread([&]() {   // symbolLoopFunc, demodulator.cpp:170-175
+                try {
+                    while (!produced) {
+                        demod->processSamples(symbolManager, diagManager);
+                        std::this_thread::sleep_for(std::chrono::microseconds(1));
+                    }
+                    while (demod->processSamples(symbolManager, diagManager, 1) > 0) {
+                    }
+                } catch (SatHelperException &e) {
+                    loopError = e.reason();
+                }
+            });
+            frontend.join();
+            symbolThread.join();
+            if (!producerError.empty() || !loopError.empty()) {
+                g_error = producerError + loopError;
+                return -1;
+            }
+        } else {
+            int blk = 0;
+            for (long long pos = 0; pos < n; pos += block, blk++) {
+                if (blk == checkpoint_at_block && blk > 0) {
+                    std::vector<unsigned char> blob = demod->checkpoint();
+                    std::unique_ptr<xrd::Demodulator> next(new xrd::Demodulator(hrit != 0));
+                    next->restore(blob);
+                    demod.swap(next);   // the old demodulator is destroyed; the restored one carries on
+                }
+                const int length = (int)std::min<long long>(block, n - pos);
+                demod->callback()((void *)((const char *)raw + bytes * (size_t)pos), length, type);
+                demod->processSamples(symbolManager, diagManager, 1);
+            }
+        }
+        const long long ns = (long long)symbolManager.symbols.size();
+        const long long nd = (long long)diagManager.floats.size();
+        if (ns > cap || nd > diagCap) {
+            g_error = "output capacity too small";
+            return -1;
+        }
+        memcpy(symOut, symbolManager.symbols.data(), sizeof(float) * 2 * (size_t)ns);
+        memcpy(diagOut, diagManager.floats.data(), sizeof(float) * (size_t)nd);
+        *nDiag = nd;
         return ns;
     } catch (SatHelperException &e) {
         g_error = e.reason();

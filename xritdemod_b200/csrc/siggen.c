@@ -13,6 +13,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -60,6 +63,18 @@ static double rrc_pulse(double t, double a)
     double num = sin(M_PI * t * (1.0 - a)) + 4.0 * a * t * cos(M_PI * t * (1.0 + a));
     double den = M_PI * t * (1.0 - 16.0 * a * a * t * t);
     return num / den;
+}
+
+/* worker threads of the generator (launchers such as torchrun export OMP_NUM_THREADS=1, which would make
+ * every rank generate its stream on one core); 0 = leave the OpenMP default */
+void xrd_siggen_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0)
+        omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 void xrd_siggen_bits(uint64_t seed, int64_t k_start, int64_t n, int8_t *out)
@@ -137,6 +152,17 @@ void xrd_cf32_to_s16(const float *in, uint64_t n_complex, int16_t *out)
         float v = rintf(in[i] * 32768.f);
         v = v > 32767.f ? 32767.f : (v < -32768.f ? -32768.f : v);
         out[i] = (int16_t)v;
+    }
+}
+
+/* cf32 -> the SpyServer / RTL-SDR u8 format (offset binary around 128) */
+void xrd_cf32_to_u8(const float *in, uint64_t n_complex, uint8_t *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)(2 * n_complex); i++) {
+        float v = rintf(in[i] * 128.f) + 128.f;
+        v = v > 255.f ? 255.f : (v < 0.f ? 0.f : v);
+        out[i] = (uint8_t)v;
     }
 }
 

@@ -4,7 +4,6 @@
 #include "../../include/xrd.h"
 #include "xrd_kernels.cuh"
 #include "xrd_wn.cuh"
-#include "xrd_mmwn.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -17,7 +16,10 @@
 
 namespace xrd {
 
-static thread_local std::string g_create_error;
+// Last error message of the calling thread (xrd_last_error / xrd_stage_last_error).  Per thread, like errno: the
+// reference wiring calls xrd_add_samples on the frontend thread and xrd_process on the symbol-loop thread
+// (demodulator.cpp:434,475), and neither may clobber a message the other is reading.
+static thread_local std::string g_error;
 
 struct CudaError {
     std::string msg;
@@ -516,8 +518,6 @@ struct MmStage {
     long long W = 800000;           // the warm-up of the current call
     long long Lmin = 262144;
     int nt = 0;                     // lanes per chain of mm_chain32_kernel (0 = auto)
-    int wn_k = 0, wn_wpc = 16;      // window-Newton chain kernel (xrd_mmwn.cuh): slots per thread, warps; 0 = mm_chain32_kernel,
-                                    // which is still ~7 % faster on B200 (fewer, cheaper instructions per symbol)
     bool force64 = false;           // tests: always use the generic 64-bit chain kernel
     int sm_count = 148;
     int nch = 1;
@@ -555,7 +555,8 @@ struct MmStage {
         s_init.omega = omega;
         d_carried.ensure(sizeof(MmState) * nch);
         reset();
-        d_nredo.ensure(2 * sizeof(int));   // [0] segments flagged by the verify pass, [1] delta re-runs that gave up
+        d_nredo.ensure(4 * sizeof(int));   // [0] segments flagged by the verify pass, [1] delta re-runs that gave up,
+                                           // [2] a chain hit its iteration cap (non-finite samples stalled the loop)
         d_overflow.ensure(sizeof(int));
         if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, 4 * sizeof(int)));
         int dev = 0;
@@ -617,32 +618,6 @@ struct MmStage {
             if (mm_chain32_smem_bytes(NT, R) <= 200 * 1024 || NT <= 128) break;
         }
         const bool fast = fast32(NT, n, Lseg, cap_seg);
-        if (fast && wn_k > 0) {
-            // window-Newton chain: K slots per thread, WPC warps (xrd_mmwn.cuh)
-            const int NTw = 32 * wn_wpc * wn_k;
-            int Rw = next_pow2((long long)(2 * NTw * adv) + 160);
-            const MmWnLayout lay(NTw, wn_wpc, Rw);
-            if (lay.total <= 220 * 1024) {
-                const int ncp = (int)(Lseg / ck_spacing) + 2;
-                d_ckpt.ensure(sizeof(MmCk) * (size_t)grid.x * grid.y * ncp);
-#define XRD_MM_WN(KV, WV)                                                                                                \
-    do {                                                                                                                 \
-        XRD_CUDA(cudaFuncSetAttribute(mm_wn_kernel<KV, WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total)); \
-        XRD_LAUNCH(c, (mm_wn_kernel<KV, WV>), grid, 32 * WV, lay.total, st, in, d_stage.as<float2>(), (int)n, (int)Lseg,  \
-                   (int)W, nseg, (int)cap_seg, d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(),     \
-                   d_redo.as<unsigned char>(), d_segout.as<MmSegOut>(), d_table.as<float>(), prm, mode, in_stride,       \
-                   stage_stride, Rw, d_ckpt.as<MmCk>(), ncp, ck_spacing);                                                \
-    } while (0)
-                if (wn_k == 2 && wn_wpc == 16) XRD_MM_WN(2, 16);
-                else if (wn_k == 4 && wn_wpc == 8) XRD_MM_WN(4, 8);
-                else if (wn_k == 4 && wn_wpc == 16) XRD_MM_WN(4, 16);
-                else if (wn_k == 2 && wn_wpc == 8) XRD_MM_WN(2, 8);
-                else if (wn_k == 1 && wn_wpc == 32) XRD_MM_WN(1, 32);
-                else XRD_MM_WN(1, 16);
-#undef XRD_MM_WN
-                return;
-            }
-        }
         if (fast) {
             const size_t smem32 = mm_chain32_smem_bytes(NT, R);
             const int ncp = (int)(Lseg / ck_spacing) + 2;
@@ -653,7 +628,7 @@ struct MmStage {
         XRD_LAUNCH(c, mm_chain32_kernel<NTV>, grid, NTV, smem32, st, in, d_stage.as<float2>(), (int)n, (int)Lseg, (int)W, \
                    nseg, (int)cap_seg, d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(),             \
                    d_redo.as<unsigned char>(), d_segout.as<MmSegOut>(), d_table.as<float>(), prm, mode, in_stride,       \
-                   stage_stride, R, d_ckpt.as<MmCk>(), ncp, ck_spacing, traj());                                         \
+                   stage_stride, R, d_ckpt.as<MmCk>(), ncp, ck_spacing, traj(), d_nredo.as<int>() + 2);                  \
     } while (0)
             if (NT >= 1024) XRD_MM_CHAIN32(1024);
             else if (NT == 512) XRD_MM_CHAIN32(512);
@@ -669,7 +644,8 @@ struct MmStage {
         XRD_CUDA(cudaFuncSetAttribute(mm_chain_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
         XRD_LAUNCH(c, mm_chain_kernel<NTV>, grid, NTV, smem, st, in, d_stage.as<float2>(), n, Lseg, W, nseg, cap_seg,  \
                    d_entry.as<MmState>(), d_exit.as<MmState>(), d_carried.as<MmState>(), d_redo.as<unsigned char>(),   \
-                   d_segout.as<MmSegOut>(), d_table.as<float>(), prm, mode, in_stride, stage_stride, R);               \
+                   d_segout.as<MmSegOut>(), d_table.as<float>(), prm, mode, in_stride, stage_stride, R,                \
+                   d_nredo.as<int>() + 2);                                                                             \
     } while (0)
         if (NT >= 1024) XRD_MM_CHAIN(1024);
         else if (NT == 512) XRD_MM_CHAIN(512);
@@ -719,12 +695,12 @@ struct MmStage {
         dim3 grid(nseg, nch);
         // record the trajectory when there are hand-offs to certify and the kernel that records it will run
         W = W_user > 0 ? W_user : 80000;
-        traj_on = use_delta && nseg > 1 && wn_k == 0 && fast32(nt ? nt : 1024, n, Ls, cap_seg);
+        traj_on = use_delta && nseg > 1 && fast32(nt ? nt : 1024, n, Ls, cap_seg);
         if (!traj_on && W_user <= 0) W = 800000;
         if (traj_on) {
             d_traj.ensure(sizeof(int4) * (size_t)cap_seg * tot);
         }
-        XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, 2 * sizeof(int), st));
+        XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, 4 * sizeof(int), st));
         launch_chain(c, st, grid, in, n, Ls, nseg, cap_seg, 0, in_stride, stage_stride);
         for (int round = 0; nseg > 1 && round < nseg; round++) {
             XRD_CUDA(cudaMemsetAsync(d_nredo.p, 0, sizeof(int), st));
@@ -732,8 +708,9 @@ struct MmStage {
             XRD_LAUNCH(c, mm_verify_kernel, vg, 128, 0, st, nseg, d_entry.as<MmState>(), d_exit.as<MmState>(),
                        d_redo.as<unsigned char>(), d_nredo.as<int>());
             XRD_CUDA(cudaMemcpyAsync(h_nredo, d_nredo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            XRD_CUDA(cudaMemcpyAsync(h_nredo + 3, d_nredo.as<int>() + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
             XRD_CUDA(cudaStreamSynchronize(st));
-            if (*h_nredo == 0) break;
+            if (*h_nredo == 0 || h_nredo[3]) break;   // closed, or a chain stalled (reported as overflow below)
             rounds++;
             redone += (uint64_t)*h_nredo;
             // the delta kernel clears the flag of every segment it finishes; the chain kernel takes what is left
@@ -780,14 +757,21 @@ using namespace xrd;
 // ---------------------------------------------------------------------------------------
 // the chain
 // ---------------------------------------------------------------------------------------
+static size_t type_bytes(int type)
+{
+    // device-side ingest formats (XRD_RTLU8IQ carries a serial DC blocker and exists on the FIFO seam only)
+    return type == XRD_FLOATIQ ? 8 : (type == XRD_S16IQ ? 4 : ((type == XRD_S8IQ || type == XRD_U8IQ) ? 2 : 0));
+}
+
+static const size_t XRD_FIFO_FLOATS = 1024 * 1024;   // FIFO_SIZE, Parameters.h:57
 struct HostFifo {
     std::vector<float> buf;   // interleaved floats, ring (CircularBuffer<float>, demodulator.cpp:38)
     size_t head = 0, count = 0;
+    float rtl_alpha = 0.f, rtl_avg = 0.f;   // DC blocker of the RTL u8 ingest (RtlFrontend.cpp:57-59,104-116)
 };
 
 struct xrd_demod {
     xrd_config cfg;
-    std::string err;
     int nch = 1, D = 1;
     float sps = 0.f;
     cudaStream_t stream = nullptr;
@@ -896,7 +880,10 @@ struct xrd_demod {
         std::fill(n_in.begin(), n_in.end(), 0);
         std::fill(n_sym.begin(), n_sym.end(), 0);
         std::lock_guard<std::mutex> lk(fifo_mu);
-        for (auto &f : fifo) f.head = f.count = 0;
+        for (auto &f : fifo) {
+            f.head = f.count = 0;
+            f.rtl_avg = 0.f;
+        }
     }
 
     // Front half of the chain (everything at the sample rate: ingest, decimator, AGC, RRC, Costas) over input
@@ -922,10 +909,13 @@ struct xrd_demod {
                                              cudaMemcpyDeviceToDevice, stream));
                 } else if (type == XRD_S16IQ) {
                     XRD_LAUNCH(ctr, (convert_kernel<short>), blocks, 256, 0, stream, (const short *)iq_dev + (size_t)ch * nf,
-                               o, nf, 1.0f / 32768.f);
-                } else {
+                               o, nf, 1.0f / 32768.f, 0.f);
+                } else if (type == XRD_S8IQ) {
                     XRD_LAUNCH(ctr, (convert_kernel<signed char>), blocks, 256, 0, stream,
-                               (const signed char *)iq_dev + (size_t)ch * nf, o, nf, 1.0f / 128.f);
+                               (const signed char *)iq_dev + (size_t)ch * nf, o, nf, 1.0f / 128.f, 0.f);
+                } else {
+                    XRD_LAUNCH(ctr, (convert_kernel<unsigned char>), blocks, 256, 0, stream,
+                               (const unsigned char *)iq_dev + (size_t)ch * nf, o, nf, 1.0f / 128.f, 128.f);
                 }
             }
             x = dst;
@@ -980,14 +970,15 @@ struct xrd_demod {
             n_in[ch] += (uint64_t)n;
             n_sym[ch] += (uint64_t)std::min<long long>(counts[ch], cap);
         }
-        if (rc == XRD_E_OVERFLOW) err = "symbol output capacity too small";
+        if (rc == XRD_E_OVERFLOW)
+            g_error = "symbol output capacity too small (or non-finite samples stalled the timing loop)";
         return rc;
     }
 
     bool check_len(long long n, int64_t *counts, int &rc)
     {
         if (n % D) {
-            err = "n_complex must be a multiple of the decimation";
+            g_error = "n_complex must be a multiple of the decimation";
             rc = XRD_E_ARG;
             return false;
         }
@@ -1017,7 +1008,7 @@ struct xrd_demod {
     {
         int rc = XRD_OK;
         if (!check_len(n, counts, rc)) return rc;
-        const size_t sb = (type == XRD_FLOATIQ) ? 8 : (type == XRD_S16IQ ? 4 : 2);
+        const size_t sb = type_bytes(type);
         b_raw.ensure(sb * (size_t)n * nch);
         ensure(n);
         for (float &v : ms) v = 0.f;
@@ -1060,21 +1051,15 @@ struct xrd_demod {
     int max_pieces = 2;             // more pieces shorten the Costas segments and cost more re-run rounds than the overlap wins
 };
 
-static size_t type_bytes(int type)
-{
-    return type == XRD_FLOATIQ ? 8 : (type == XRD_S16IQ ? 4 : (type == XRD_S8IQ ? 2 : 0));
-}
-
-template <class F> static int guarded(std::string *err, F &&f)
+template <class F> static int guarded(F &&f)
 {
     try {
         return f();
     } catch (const CudaError &e) {
-        if (err) *err = e.msg;
-        else g_create_error = e.msg;
+        g_error = e.msg;
         return e.code;
     } catch (const std::bad_alloc &) {
-        if (err) *err = "host allocation failed";
+        g_error = "host allocation failed";
         return XRD_E_NOMEM;
     }
 }
@@ -1084,16 +1069,16 @@ static int select_device(int dev)
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
-        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        g_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
         return XRD_E_CUDA;
     }
     if (dev < 0 || dev >= n) {
-        g_create_error = "device ordinal out of range";
+        g_error = "device ordinal out of range";
         return XRD_E_ARG;
     }
     e = cudaSetDevice(dev);
     if (e != cudaSuccess) {
-        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        g_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
         return XRD_E_CUDA;
     }
     return XRD_OK;
@@ -1142,17 +1127,17 @@ int xrd_create(const xrd_config *cfg, xrd_demod **out)
     if (!cfg || !out) return XRD_E_ARG;
     *out = nullptr;
     if (cfg->n_channels < 1 || cfg->symbol_rate == 0 || cfg->sample_rate == 0 || cfg->rrc_taps < 1) {
-        g_create_error = "bad config";
+        g_error = "bad config";
         return XRD_E_ARG;
     }
     if (cfg->loop_order != 2) {
-        g_create_error = "only loop_order 2 (BPSK) is implemented";
+        g_error = "only loop_order 2 (BPSK) is implemented";
         return XRD_E_ARG;
     }
     int rc = select_device(cfg->device_ordinal);
     if (rc) return rc;
     xrd_demod *d = new xrd_demod();
-    rc = guarded(nullptr, [&]() {
+    rc = guarded([&]() {
         d->cfg = *cfg;
         d->nch = cfg->n_channels;
         d->D = cfg->decimation ? (int)cfg->decimation : 1;
@@ -1189,6 +1174,7 @@ int xrd_create(const xrd_config *cfg, xrd_demod **out)
         d->n_in.assign(d->nch, 0);
         d->n_sym.assign(d->nch, 0);
         d->fifo.resize(d->nch);
+        for (auto &f : d->fifo) f.rtl_alpha = (float)(1.f - exp(-1.0 / (cfg->sample_rate * 0.05f)));   // RtlFrontend.cpp:57
         return (int)XRD_OK;
     });
     if (rc) {
@@ -1206,13 +1192,13 @@ void xrd_destroy(xrd_demod *d)
     delete d;
 }
 
-const char *xrd_last_error(const xrd_demod *d) { return d ? d->err.c_str() : g_create_error.c_str(); }
+const char *xrd_last_error(const xrd_demod *) { return g_error.c_str(); }
 
 int xrd_demod_device(xrd_demod *d, const void *iq_dev, size_t n_complex, int type, float *sym_dev, size_t cap,
                      int64_t *n_sym)
 {
     if (!d || !iq_dev || !sym_dev || !n_sym || !type_bytes(type)) return XRD_E_ARG;
-    return guarded(&d->err, [&]() {
+    return guarded([&]() {
         XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
         return d->run_device(iq_dev, (long long)n_complex, type, (float2 *)sym_dev, (long long)cap, n_sym);
     });
@@ -1222,7 +1208,7 @@ int xrd_demod_batch(xrd_demod *d, const void *iq, size_t n_complex, int type, fl
                     int64_t *n_sym)
 {
     if (!d || !iq || !sym_out || !n_sym || !type_bytes(type)) return XRD_E_ARG;
-    return guarded(&d->err, [&]() {
+    return guarded([&]() {
         XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
         d->b_sym.ensure(sizeof(float2) * cap * d->nch);
         int rc = d->run_host(iq, (long long)n_complex, type, d->b_sym.as<float2>(), (long long)cap, n_sym);
@@ -1241,7 +1227,7 @@ int xrd_demod_batch_i8(xrd_demod *d, const void *iq, size_t n_complex, int type,
                        int64_t *n_sym)
 {
     if (!d || !iq || !soft_out || !n_sym || !type_bytes(type)) return XRD_E_ARG;
-    return guarded(&d->err, [&]() {
+    return guarded([&]() {
         XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
         d->b_i8.ensure(cap * d->nch);
         // the M&M compaction writes the bytes itself; no cf32 symbol stream is materialised
@@ -1265,31 +1251,68 @@ int xrd_demod_batch_i8(xrd_demod *d, const void *iq, size_t n_complex, int type,
     });
 }
 
+// onSamplesAvailable's conversions (demodulator.cpp:56-70) plus the two u8 formats the reference's front ends convert
+// themselves before calling it: SpyServer (SpyServerFrontend.cpp:404-407) and RTL-SDR (RtlFrontend.cpp:27,104-116)
+static void convert_to_fifo(float *dst, const void *data, size_t first, size_t count, int type, HostFifo &f)
+{
+    switch (type) {
+    case XRD_FLOATIQ:
+        memcpy(dst, (const float *)data + first, sizeof(float) * count);
+        break;
+    case XRD_S16IQ: {
+        const int16_t *p = (const int16_t *)data + first;
+        for (size_t i = 0; i < count; i++) dst[i] = p[i] / 32768.f;   // demodulator.cpp:60-61
+        break;
+    }
+    case XRD_S8IQ: {
+        const int8_t *p = (const int8_t *)data + first;
+        for (size_t i = 0; i < count; i++) dst[i] = p[i] / 128.f;     // demodulator.cpp:67-68
+        break;
+    }
+    case XRD_U8IQ: {
+        const uint8_t *p = (const uint8_t *)data + first;
+        for (size_t i = 0; i < count; i++) dst[i] = (p[i] - 128) / 128.f;   // SpyServerFrontend.cpp:406
+        break;
+    }
+    default: {   // XRD_RTLU8IQ
+        // RtlFrontend::internalCallback: lut[v] = (v - 128) * (1.f / 127.f), then a one-pole DC blocker.  The
+        // reference tests `i % 1`, which is never true, so EVERY float (I and Q alike) runs through the one
+        // average `iavg`; that is reproduced as is.
+        const uint8_t *p = (const uint8_t *)data + first;
+        float avg = f.rtl_avg;
+        const float alpha = f.rtl_alpha;
+        for (size_t i = 0; i < count; i++) {
+            float v = ((int)p[i] - 128) * (1.f / 127.f);
+            avg += alpha * (v - avg);
+            v -= avg;
+            dst[i] = v;
+        }
+        f.rtl_avg = avg;
+        break;
+    }
+    }
+}
+
 int xrd_add_samples(xrd_demod *d, int channel, const void *data, int n_complex, int type)
 {
     if (!d || channel < 0 || channel >= d->nch || n_complex < 0 || (!data && n_complex)) return XRD_E_ARG;
-    if (type != XRD_FLOATIQ && type != XRD_S16IQ && type != XRD_S8IQ) {
-        d->err = "Unknown sample type";   // demodulator.cpp:71-73
+    if (type < XRD_FLOATIQ || type > XRD_RTLU8IQ) {
+        g_error = "Unknown sample type";   // demodulator.cpp:71-73
         return XRD_E_ARG;
     }
     std::lock_guard<std::mutex> lk(d->fifo_mu);
     HostFifo &f = d->fifo[channel];
-    const size_t FIFO = 1024 * 1024;   // FIFO_SIZE floats, Parameters.h:57
-    if (f.buf.empty()) f.buf.resize(FIFO);
+    if (f.buf.empty()) f.buf.resize(XRD_FIFO_FLOATS);
     const size_t nf = (size_t)n_complex * 2;
-    if (f.count + nf > FIFO) {
-        d->err = "Input Samples Fifo is overflowing!";   // demodulator.cpp:104-106
+    if (f.count + nf > XRD_FIFO_FLOATS) {
+        g_error = "Input Samples Fifo is overflowing!";   // demodulator.cpp:104-106
         return XRD_E_OVERFLOW;
     }
-    size_t w = (f.head + f.count) % FIFO;
-    for (size_t i = 0; i < nf; i++) {
-        float v;
-        if (type == XRD_FLOATIQ) v = ((const float *)data)[i];
-        else if (type == XRD_S16IQ) v = ((const int16_t *)data)[i] / 32768.f;   // demodulator.cpp:60-61
-        else v = ((const int8_t *)data)[i] / 128.f;                              // demodulator.cpp:67-68
-        f.buf[w] = v;
-        w = (w + 1 == FIFO) ? 0 : w + 1;
-    }
+    // two spans of the ring, converted in bulk (the reference pushes float by float under its mutex)
+    const size_t w = (f.head + f.count) % XRD_FIFO_FLOATS;
+    const size_t first = std::min(nf, XRD_FIFO_FLOATS - w);
+    convert_to_fifo(f.buf.data() + w, data, 0, first, type, f);
+    if (nf > first) convert_to_fifo(f.buf.data(), data, first, nf - first, type, f);
     f.count += nf;
     return XRD_OK;
 }
@@ -1297,9 +1320,8 @@ int xrd_add_samples(xrd_demod *d, int channel, const void *data, int n_complex, 
 int64_t xrd_process(xrd_demod *d, int64_t min_samples, xrd_symbols_cb cb, void *user)
 {
     if (!d) return XRD_E_ARG;
-    return guarded(&d->err, [&]() -> int {
+    return guarded([&]() -> int {
         XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
-        const size_t FIFO = 1024 * 1024;
         size_t n = 0;
         {
             std::lock_guard<std::mutex> lk(d->fifo_mu);
@@ -1311,35 +1333,48 @@ int64_t xrd_process(xrd_demod *d, int64_t min_samples, xrd_symbols_cb cb, void *
             if (bytes > d->h_pin_bytes) {
                 if (d->h_pin) cudaFreeHost(d->h_pin);
                 d->h_pin = nullptr;
+                d->h_pin_bytes = 0;
                 XRD_CUDA(cudaMallocHost(&d->h_pin, bytes));
                 d->h_pin_bytes = bytes;
             }
+            // copy out, but leave the samples queued until the chain has succeeded on them
             float *dst = (float *)d->h_pin;
             for (int ch = 0; ch < d->nch; ch++) {
-                HostFifo &f = d->fifo[ch];
-                for (size_t i = 0; i < 2 * n; i++) {
-                    dst[(size_t)ch * 2 * n + i] = f.buf[f.head];
-                    f.head = (f.head + 1 == FIFO) ? 0 : f.head + 1;
-                }
-                f.count -= 2 * n;
+                const HostFifo &f = d->fifo[ch];
+                const size_t first = std::min(2 * n, XRD_FIFO_FLOATS - f.head);
+                memcpy(dst + (size_t)ch * 2 * n, f.buf.data() + f.head, sizeof(float) * first);
+                if (2 * n > first) memcpy(dst + (size_t)ch * 2 * n + first, f.buf.data(), sizeof(float) * (2 * n - first));
             }
         }
         const size_t cap = (size_t)d->mm.max_symbols((long long)(n / d->D));
         d->h_sym.resize(2 * cap * d->nch);
         d->h_cnt.assign(d->nch, 0);
         int rc = xrd_demod_batch(d, d->h_pin, n, XRD_FLOATIQ, d->h_sym.data(), cap, d->h_cnt.data());
-        if (rc) return rc;
+        if (rc) return rc;   // nothing was dequeued; the loop state may have advanced: xrd_reset before retrying
+        {
+            std::lock_guard<std::mutex> lk(d->fifo_mu);
+            for (auto &f : d->fifo) {
+                f.head = (f.head + 2 * n) % XRD_FIFO_FLOATS;
+                f.count -= 2 * n;
+            }
+        }
         if (cb)
             for (int ch = 0; ch < d->nch; ch++) cb(user, ch, d->h_sym.data() + 2 * cap * ch, (int)d->h_cnt[ch]);
         return (int)n;
     });
 }
 
+int64_t xrd_symbol_capacity(const xrd_demod *d, size_t n_complex)
+{
+    if (!d) return XRD_E_ARG;
+    return (int64_t)d->mm.max_symbols((long long)(n_complex / (size_t)d->D));
+}
+
 int xrd_soft_i8(xrd_demod *d, const float *sym, size_t n, int8_t *out)
 {
     if (!d || (!sym && n) || (!out && n)) return XRD_E_ARG;
     if (!n) return XRD_OK;
-    return guarded(&d->err, [&]() {
+    return guarded([&]() {
         XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
         d->b_sym.ensure(sizeof(float2) * n);
         d->b_i8.ensure(n);
@@ -1356,7 +1391,7 @@ int xrd_soft_i8(xrd_demod *d, const float *sym, size_t n, int8_t *out)
 int xrd_reset(xrd_demod *d)
 {
     if (!d) return XRD_E_ARG;
-    return guarded(&d->err, [&]() {
+    return guarded([&]() {
         XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
         d->reset();
         return (int)XRD_OK;
@@ -1368,7 +1403,7 @@ void *xrd_stream(xrd_demod *d) { return d ? (void *)d->stream : nullptr; }
 int xrd_get_state(xrd_demod *d, int channel, xrd_loop_state *st)
 {
     if (!d || !st || channel < 0 || channel >= d->nch) return XRD_E_ARG;
-    return guarded(&d->err, [&]() {
+    return guarded([&]() {
         XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
         XRD_CUDA(cudaStreamSynchronize(d->stream));
         AgcState a = d->agc.get(channel);
@@ -1390,44 +1425,173 @@ int xrd_get_state(xrd_demod *d, int channel, xrd_loop_state *st)
     });
 }
 
+int xrd_set_state(xrd_demod *d, int channel, const xrd_loop_state *st)
+{
+    if (!d || !st || channel < 0 || channel >= d->nch) return XRD_E_ARG;
+    return guarded([&]() {
+        XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
+        XRD_CUDA(cudaStreamSynchronize(d->stream));
+        const AgcState a{st->agc_gain, 0.f};
+        const CostasState c{st->costas_phase, st->costas_freq};
+        MmState m;
+        m.ii = st->mm_next;
+        m.mu = st->mm_mu;
+        m.omega = st->mm_omega;
+        m.p0 = make_float2(st->mm_p0[0], st->mm_p0[1]);
+        m.p1 = make_float2(st->mm_p1[0], st->mm_p1[1]);
+        XRD_CUDA(cudaMemcpy(d->agc.d_carried.as<AgcState>() + channel, &a, sizeof a, cudaMemcpyHostToDevice));
+        XRD_CUDA(cudaMemcpy(d->costas.d_carried.as<CostasState>() + channel, &c, sizeof c, cudaMemcpyHostToDevice));
+        XRD_CUDA(cudaMemcpy(d->mm.d_carried.as<MmState>() + channel, &m, sizeof m, cudaMemcpyHostToDevice));
+        d->n_in[channel] = st->n_in;
+        d->n_sym[channel] = st->n_sym;
+        return (int)XRD_OK;
+    });
+}
+
+// ---- checkpoint: everything the five operators hold between calls, all channels ----
+namespace {
+struct CkptHeader {
+    uint32_t magic, version, nch, D, Hd, Hr, tail, reserved;
+    xrd_config cfg;
+};
+const uint32_t CKPT_MAGIC = 0x43445258u;   // "XRDC"
+size_t ckpt_bytes(const xrd_demod *d)
+{
+    const size_t Hd = (d->D > 1) ? (size_t)d->dec.hist() : 0, Hr = (size_t)d->rrc.hist();
+    return sizeof(CkptHeader) + (size_t)d->nch * (sizeof(xrd_loop_state) + sizeof(float) + sizeof(float2) * (Hd + Hr + MM_TAIL));
+}
+}  // namespace
+
+size_t xrd_checkpoint_size(const xrd_demod *d) { return d ? ckpt_bytes(d) : 0; }
+
+int xrd_checkpoint_save(xrd_demod *d, void *blob, size_t cap)
+{
+    if (!d || !blob) return XRD_E_ARG;
+    if (cap < ckpt_bytes(d)) return XRD_E_OVERFLOW;
+    return guarded([&]() {
+        XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
+        XRD_CUDA(cudaStreamSynchronize(d->stream));
+        const int Hd = (d->D > 1) ? d->dec.hist() : 0, Hr = d->rrc.hist();
+        CkptHeader h;
+        memset(&h, 0, sizeof h);
+        h.magic = CKPT_MAGIC;
+        h.version = 1;
+        h.nch = (uint32_t)d->nch;
+        h.D = (uint32_t)d->D;
+        h.Hd = (uint32_t)Hd;
+        h.Hr = (uint32_t)Hr;
+        h.tail = MM_TAIL;
+        h.cfg = d->cfg;
+        char *p = (char *)blob;
+        memcpy(p, &h, sizeof h);
+        p += sizeof h;
+        for (int ch = 0; ch < d->nch; ch++) {
+            xrd_loop_state st;
+            int rc = xrd_get_state(d, ch, &st);
+            if (rc) return rc;
+            memcpy(p, &st, sizeof st);
+            p += sizeof st;
+            float avg;
+            {
+                std::lock_guard<std::mutex> lk(d->fifo_mu);
+                avg = d->fifo[ch].rtl_avg;
+            }
+            memcpy(p, &avg, sizeof avg);
+            p += sizeof avg;
+            // histories live in the prefixes of the chunk buffers; all zero before the first call
+            auto grab = [&](const DevBuf &b, long long stride, int count) {
+                if (count <= 0) return;
+                if (d->cap_n > 0) XRD_CUDA(cudaMemcpy(p, b.as<float2>() + (size_t)ch * stride, sizeof(float2) * count, cudaMemcpyDeviceToHost));
+                else memset(p, 0, sizeof(float2) * count);
+                p += sizeof(float2) * count;
+            };
+            grab(d->b_in, d->in_stride(), Hd);
+            grab(d->b_agc, d->agc_stride(), Hr);
+            grab(d->b_cos, d->cos_stride(), MM_TAIL);
+        }
+        return (int)XRD_OK;
+    });
+}
+
+int xrd_checkpoint_load(xrd_demod *d, const void *blob, size_t bytes)
+{
+    if (!d || !blob || bytes < sizeof(CkptHeader)) return XRD_E_ARG;
+    CkptHeader h;
+    memcpy(&h, blob, sizeof h);
+    const int Hd = (d->D > 1) ? d->dec.hist() : 0, Hr = d->rrc.hist();
+    xrd_config a = h.cfg, b = d->cfg;
+    a.device_ordinal = b.device_ordinal = 0;   // a checkpoint may move between devices
+    if (h.magic != CKPT_MAGIC || h.version != 1 || (int)h.nch != d->nch || (int)h.D != d->D || (int)h.Hd != Hd ||
+        (int)h.Hr != Hr || h.tail != MM_TAIL || memcmp(&a, &b, sizeof a) != 0 || bytes < ckpt_bytes(d)) {
+        g_error = "checkpoint does not belong to a demodulator with this configuration";
+        return XRD_E_STATE;
+    }
+    return guarded([&]() {
+        XRD_CUDA(cudaSetDevice(d->cfg.device_ordinal));
+        XRD_CUDA(cudaStreamSynchronize(d->stream));
+        d->ensure(std::max<long long>(d->cap_n, 1024LL * d->D));
+        const char *p = (const char *)blob + sizeof h;
+        for (int ch = 0; ch < d->nch; ch++) {
+            xrd_loop_state st;
+            memcpy(&st, p, sizeof st);
+            p += sizeof st;
+            int rc = xrd_set_state(d, ch, &st);
+            if (rc) return rc;
+            float avg;
+            memcpy(&avg, p, sizeof avg);
+            p += sizeof avg;
+            {
+                std::lock_guard<std::mutex> lk(d->fifo_mu);
+                d->fifo[ch].rtl_avg = avg;
+            }
+            auto put = [&](DevBuf &buf, long long stride, int count) {
+                if (count <= 0) return;
+                XRD_CUDA(cudaMemcpy(buf.as<float2>() + (size_t)ch * stride, p, sizeof(float2) * count, cudaMemcpyHostToDevice));
+                p += sizeof(float2) * count;
+            };
+            put(d->b_in, d->in_stride(), Hd);
+            put(d->b_agc, d->agc_stride(), Hr);
+            put(d->b_cos, d->cos_stride(), MM_TAIL);
+        }
+        return (int)XRD_OK;
+    });
+}
+
 int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
 {
     if (!d || !t) return XRD_E_ARG;
     if (t->agc_seg < 0 || t->agc_warm < 0 || t->costas_seg < 0 || t->costas_warm < 0 || t->mm_seg < 0 || t->mm_warm < 0)
+        return XRD_E_ARG;
+    auto lanes_ok = [](int v, int lo) { return v == 0 || (v >= lo && v <= 1024 && (v & (v - 1)) == 0); };
+    if (!lanes_ok(t->mm_lanes, 128) || !lanes_ok(t->mm_walk_lanes, 128) || t->mm_walk_lanes > 512) return XRD_E_ARG;
+    if (t->mm_kernel < 0 || t->mm_kernel > 2 || t->mm_rerun < 0 || t->mm_rerun > 2) return XRD_E_ARG;
+    if (t->loop_kernel < 0 || t->loop_kernel > 7 || t->rerun_kernel < 0 || t->rerun_kernel == 1 || t->rerun_kernel > 7)
+        return XRD_E_ARG;
+    if (t->h2d_pieces < 0 || t->h2d_pieces > 16 || t->h2d_piece_min_ki < 0) return XRD_E_ARG;
+    if (t->costas_chains_per_sm < 0 || t->costas_chains_per_sm > 64 || t->agc_chains_per_sm < 0 || t->agc_chains_per_sm > 64)
         return XRD_E_ARG;
     if (t->agc_seg) d->agc.L = d->agc.Lw = t->agc_seg;
     if (t->agc_warm) d->agc.W = d->agc.Ww = t->agc_warm;
     if (t->costas_seg) d->costas.L = d->costas.Lw = t->costas_seg;
     if (t->costas_warm) d->costas.W = d->costas.Ww = t->costas_warm;
     if (t->loop_kernel == 1) d->agc.use_wn = d->costas.use_wn = false;
-    else if ((t->loop_kernel & 0xff) >= 2 && (t->loop_kernel & 0xff) <= 7 && (t->loop_kernel >> 8) <= 7) {
+    else if (t->loop_kernel) {
         d->agc.use_wn = agc_wn_ok(d->agc.prm.max_gain);
         d->costas.use_wn = costas_wn_ok(d->costas.prm);
-        d->agc.wn_variant = d->costas.wn_variant = t->loop_kernel & 0xff;
-        d->agc.redo_variant = d->costas.redo_variant = (t->loop_kernel >> 8) ? (t->loop_kernel >> 8) : (t->loop_kernel & 0xff);
-    } else if (t->loop_kernel) return XRD_E_ARG;
-    if (t->reserved > 0) d->costas.chains_per_sm = t->reserved & 0xff;
-    if ((t->reserved >> 8) > 0) d->agc.chains_per_sm = (t->reserved >> 8) & 0xff;
+        d->agc.wn_variant = d->costas.wn_variant = t->loop_kernel;
+        d->agc.redo_variant = d->costas.redo_variant = t->loop_kernel;   // unless rerun_kernel says otherwise below
+    }
+    if (t->rerun_kernel) d->agc.redo_variant = d->costas.redo_variant = t->rerun_kernel;
+    if (t->costas_chains_per_sm) d->costas.chains_per_sm = t->costas_chains_per_sm;
+    if (t->agc_chains_per_sm) d->agc.chains_per_sm = t->agc_chains_per_sm;
     if (t->mm_seg) d->mm.L = std::max<long long>(t->mm_seg, 64);
-    if (t->mm_lanes & 0x20000) {   // window-Newton chain with (slots per thread << 8 | warps)
-        d->mm.wn_k = (t->mm_lanes >> 8) & 0xff;
-        d->mm.wn_wpc = t->mm_lanes & 0xff;
-    } else if (t->mm_lanes & 0xffff) {   // mm_chain32_kernel with that many lanes (+0x10000: the generic 64-bit kernel)
-        d->mm.nt = t->mm_lanes & 0xffff;
-        d->mm.wn_k = 0;
-    }
-    d->mm.force64 = (t->mm_lanes & 0x10000) != 0;
-    d->mm.use_delta = (t->mm_lanes & 0x40000) == 0;
-    switch ((t->mm_lanes >> 20) & 0xf) {
-    case 1: d->mm.delta_nt = 128; break;
-    case 2: d->mm.delta_nt = 256; break;
-    case 3: d->mm.delta_nt = 512; break;
-    default: break;
-    }
+    if (t->mm_lanes) d->mm.nt = t->mm_lanes;
+    if (t->mm_kernel) d->mm.force64 = (t->mm_kernel == 2);
+    if (t->mm_rerun) d->mm.use_delta = (t->mm_rerun == 1);
+    if (t->mm_walk_lanes) d->mm.delta_nt = t->mm_walk_lanes;
     if (t->mm_warm) d->mm.W_user = t->mm_warm;
-    if (t->h2d_pieces < 0) return XRD_E_ARG;
-    if (t->h2d_pieces & 0xff) d->max_pieces = t->h2d_pieces & 0xff;
-    if (t->h2d_pieces >> 8) d->piece_min = (long long)(t->h2d_pieces >> 8) * 1024;
+    if (t->h2d_pieces) d->max_pieces = t->h2d_pieces;
+    if (t->h2d_piece_min_ki) d->piece_min = (long long)t->h2d_piece_min_ki * 1024;
     return XRD_OK;
 }
 
@@ -1487,7 +1651,6 @@ void xrd_costas_gains(float bw, float *a, float *b) { costas_gains(bw, *a, *b); 
 struct xrd_stage {
     enum Kind { FIR, AGC, COSTAS, MM } kind;
     int device = 0;
-    std::string err;
     cudaStream_t stream = nullptr;
     Counters ctr;
     FirStage fir;
@@ -1538,7 +1701,7 @@ int xrd_fir_create(int device, unsigned decimation, const float *taps, int ntaps
     xrd_stage *s = nullptr;
     int rc = stage_new(device, xrd_stage::FIR, out, s);
     if (rc) return rc;
-    rc = guarded(nullptr, [&]() {
+    rc = guarded([&]() {
         XRD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         s->fir.init(decimation, taps, ntaps);
         s->prefix = ntaps - 1;
@@ -1554,7 +1717,7 @@ int xrd_agc_create(int device, float rate, float reference, float gain, float ma
     xrd_stage *s = nullptr;
     int rc = stage_new(device, xrd_stage::AGC, out, s);
     if (rc) return rc;
-    rc = guarded(nullptr, [&]() {
+    rc = guarded([&]() {
         XRD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         s->agc.prm = AgcParams{rate, reference, max_gain};
         s->agc.L = 2048;
@@ -1573,13 +1736,13 @@ int xrd_agc_create(int device, float rate, float reference, float gain, float ma
 int xrd_costas_create(int device, float loop_bw, int order, xrd_stage **out)
 {
     if (order != 2) {
-        g_create_error = "only order 2 (BPSK) is implemented";
+        g_error = "only order 2 (BPSK) is implemented";
         return XRD_E_ARG;
     }
     xrd_stage *s = nullptr;
     int rc = stage_new(device, xrd_stage::COSTAS, out, s);
     if (rc) return rc;
-    rc = guarded(nullptr, [&]() {
+    rc = guarded([&]() {
         XRD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         float a, b;
         costas_gains(loop_bw, a, b);
@@ -1602,7 +1765,7 @@ int xrd_clock_recovery_create(int device, float omega, float gain_omega, float m
     xrd_stage *s = nullptr;
     int rc = stage_new(device, xrd_stage::MM, out, s);
     if (rc) return rc;
-    rc = guarded(nullptr, [&]() {
+    rc = guarded([&]() {
         XRD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         s->mm.init(1, omega, gain_omega, mu, gain_mu, omega_rel_limit);
         s->prefix = MM_TAIL;
@@ -1617,7 +1780,7 @@ int xrd_stage_work(xrd_stage *s, const float *in, float *out, int length)
 {
     if (!s || length < 0 || (length && (!in || !out))) return XRD_E_ARG;
     if (length == 0) return 0;
-    return guarded(&s->err, [&]() -> int {
+    return guarded([&]() -> int {
         XRD_CUDA(cudaSetDevice(s->device));
         const long long n_out = length;
         const long long n_in = (s->kind == xrd_stage::FIR) ? n_out * s->fir.D : n_out;
@@ -1641,7 +1804,7 @@ int xrd_stage_work(xrd_stage *s, const float *in, float *out, int length)
             int64_t cnt = 0;
             int rc = s->mm.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_in, out_cap, 0, 0, &cnt);
             if (rc) {
-                s->err = "symbol staging overflow";
+                g_error = "symbol staging overflow";
                 return rc;
             }
             ret = (int)cnt;
@@ -1697,6 +1860,6 @@ void xrd_stage_destroy(xrd_stage *s)
     delete s;
 }
 
-const char *xrd_stage_last_error(const xrd_stage *s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+const char *xrd_stage_last_error(const xrd_stage *) { return g_error.c_str(); }
 
 }  // extern "C"

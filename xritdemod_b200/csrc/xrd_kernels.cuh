@@ -70,15 +70,16 @@ __device__ __forceinline__ void nco_sincos(float x, float &sn, float &cs)
 }
 
 // ---------------------------------------------------------------------------------------
-// ingest: S16IQ / S8IQ -> cf32 (reference demodulator.cpp:57-70: v / 32768.f, v / 128.f)
+// ingest: S16IQ / S8IQ -> cf32 (reference demodulator.cpp:57-70: v / 32768.f, v / 128.f) and the SpyServer
+// u8 format ((v - 128) / 128.f, SpyServerFrontend.cpp:406)
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void convert_kernel(const T *__restrict__ in, float *__restrict__ out, size_t n_floats, float scale)
+__global__ void convert_kernel(const T *__restrict__ in, float *__restrict__ out, size_t n_floats, float scale, float bias)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n_floats; i += stride)
-        out[i] = (float)in[i] * scale;   // scale is a power of two: identical to the division
+        out[i] = ((float)in[i] - bias) * scale;   // small integers and a power-of-two scale: identical to the division
 }
 
 // ---------------------------------------------------------------------------------------
@@ -294,7 +295,12 @@ struct AgcLoop {
         return y;
     }
     __device__ static __forceinline__ float2 step_sel(State &s, const Params &p, float2 x) { return step(s, p, x); }
-    __device__ static __forceinline__ bool same(const State &a, const State &b) { return a.gain == b.gain; }
+    // bitwise: certification is bit for bit (+0 / -0 differ), and a NaN state (non-finite input) equals itself, so
+    // the window kernels keep advancing on it instead of never accepting a slot
+    __device__ static __forceinline__ bool same(const State &a, const State &b)
+    {
+        return __float_as_uint(a.gain) == __float_as_uint(b.gain);
+    }
     // speculative start: the gain that puts the mean level of the first samples on the reference
     __device__ static __forceinline__ State guess(const Params &p, const float2 *x, int m)
     {
@@ -363,7 +369,8 @@ struct CostasLoopK {
     }
     __device__ static __forceinline__ bool same(const State &a, const State &b)
     {
-        return (a.phase == b.phase) & (a.freq == b.freq);
+        // bitwise (see AgcLoop::same)
+        return (__float_as_uint(a.phase) == __float_as_uint(b.phase)) & (__float_as_uint(a.freq) == __float_as_uint(b.freq));
     }
     __device__ static __forceinline__ State guess(const Params &, const float2 *, int)
     {
@@ -544,17 +551,19 @@ __global__ void seg_verify_kernel(int nseg, typename LOOP::State *__restrict__ e
 }
 
 // ---------------------------------------------------------------------------------------
-// Mueller & Mueller clock recovery (ClockRecovery::Work): one warp per segment.
+// Mueller & Mueller clock recovery (ClockRecovery::Work).
 //
 // The loop state is (ii, mu, omega) plus the two previous interpolants.  mu and omega stay on
 // a fixed binary grid (mu+omega never leaves one binade), so the state advances by *integer*
-// increments that depend on the state only through the symbol's timing-error value.  A warp
-// therefore solves a window of 32 consecutive symbols as a fixed point: lane i holds a believed
-// state for symbol i, applies the literal sequential transition to it, the per-lane increments
-// are prefix-summed exactly (int64 fixed point, 2^-32 sample units) into new believed states,
-// and the window is accepted when no believed state changes.  At the fixed point every lane
-// applied the true transition to the true state, so the result is the sequential trajectory
-// bit for bit; lane m is exact after m iterations, so termination is guaranteed.
+// increments that depend on the state only through the symbol's timing-error value.  A window
+// of consecutive symbols is therefore solved as a fixed point: lane i holds a believed state for
+// symbol i, applies the literal sequential transition to it, the per-lane increments are
+// prefix-summed exactly (fixed point, 2^-32 sample units) into new believed states, and lanes are
+// accepted when their believed state did not change.  At the fixed point every lane applied the
+// true transition to the true state, so the result is the sequential trajectory bit for bit;
+// lane m is exact after m iterations, so termination is guaranteed for finite samples (a
+// non-finite sample stops the advance of the loop itself; the chain kernels then stop at their
+// iteration cap and report overflow).
 // ---------------------------------------------------------------------------------------
 constexpr int MM_NTAPS = 8;
 constexpr int MM_NSTEPS = 128;
@@ -571,8 +580,10 @@ struct MmState {
 
 __device__ __forceinline__ bool mm_same(const MmState &a, const MmState &b)
 {
-    return a.ii == b.ii && a.mu == b.mu && a.omega == b.omega && a.p0.x == b.p0.x && a.p0.y == b.p0.y &&
-           a.p1.x == b.p1.x && a.p1.y == b.p1.y;
+    return a.ii == b.ii && __float_as_uint(a.mu) == __float_as_uint(b.mu) &&
+           __float_as_uint(a.omega) == __float_as_uint(b.omega) && __float_as_uint(a.p0.x) == __float_as_uint(b.p0.x) &&
+           __float_as_uint(a.p0.y) == __float_as_uint(b.p0.y) && __float_as_uint(a.p1.x) == __float_as_uint(b.p1.x) &&
+           __float_as_uint(a.p1.y) == __float_as_uint(b.p1.y);
 }
 
 // s_tab: transposed MMSE table, s_tab[j * 129 + k] = taps[k][j]
@@ -638,179 +649,6 @@ struct MmTraj {
                     // w: interpolator row rint(mu * 128)
 };
 
-// mode 0: first pass (warm-up from a speculative state, or from `carried` when the warm-up reaches
-// the chunk start); mode 1: re-run of segments flagged in `redo` from entry[j].
-__global__ void __launch_bounds__(32)
-mm_seg_kernel(const float2 *__restrict__ in /* index 0 = first new sample; MM_TAIL before it valid */,
-              float2 *__restrict__ stage, long long n, long long L, long long W, int nseg, long long cap_seg,
-              MmState *__restrict__ entry, MmState *__restrict__ exit_, const MmState *__restrict__ carried,
-              const unsigned char *__restrict__ redo, MmSegOut *__restrict__ segout, const float *__restrict__ table,
-              MmParams prm, int mode, long long in_ch_stride, long long stage_ch_stride)
-{
-    __shared__ float s_tab[8 * 129];
-    const int lane = threadIdx.x;
-    const int j = blockIdx.x;
-    const int ch = blockIdx.y;
-    in += (size_t)ch * in_ch_stride;
-    stage += (size_t)ch * stage_ch_stride + (size_t)j * cap_seg;
-    entry += (size_t)ch * nseg;
-    exit_ += (size_t)ch * nseg;
-    segout += (size_t)ch * nseg;
-    if (mode == 1 && !redo[(size_t)ch * nseg + j]) return;
-    for (int i = lane; i < 129 * 8; i += 32) {
-        const int k = i >> 3, t = i & 7;
-        s_tab[t * 129 + k] = table[i];
-    }
-    __syncwarp();
-
-    const long long seg0 = (j == 0) ? -(1LL << 62) : (long long)j * L;  // emit symbols with ii >= seg0 ...
-    const long long seg1 = (j == nseg - 1) ? (1LL << 62) : (long long)(j + 1) * L;  // ... and ii < seg1
-    MmState st;
-    bool have_entry;
-    if (mode == 0) {
-        const long long begin = (long long)j * L - W;
-        if (j == 0 || begin <= 0) {
-            st = carried[ch];
-        } else {
-            st.ii = begin;
-            st.mu = 0.5f;
-            st.omega = prm.omega_mid;
-            st.p0 = make_float2(0.f, 0.f);
-            st.p1 = make_float2(0.f, 0.f);
-        }
-        have_entry = false;
-    } else {
-        st = entry[j];
-        have_entry = true;
-    }
-    // base state of the current window (warp-uniform)
-    long long Tb = st.ii * 4294967296LL + (long long)(st.mu * MM_FIX);
-    long long Wb = (long long)(st.omega * MM_FIX);
-    float2 P1 = st.p0, P2 = st.p1;
-    int count = 0, overflow = 0, iters = 0, windows = 0;
-    const long long last_ok = n - MM_NTAPS;   // symbol computable iff ii <= last_ok
-
-    for (;;) {
-        // believed states: linear extrapolation with mm = 0
-        long long T = Tb + (long long)lane * Wb;
-        long long Wf = Wb;
-        float2 p0;
-        long long iT = 0, iW = 0;   // inclusive prefix sums of the increments
-        for (;;) {
-            iters++;
-            long long ii = T >> 32;
-            float mu = (float)(unsigned int)(T & 0xffffffffLL) * MM_UNFIX;
-            float om = (float)Wf * MM_UNFIX;
-            long long iic = min(max(ii, (long long)-MM_TAIL), last_ok);   // keep loads in bounds
-            p0 = mm_interp(in + iic, s_tab, mu);
-            float2 p1, p2;
-            p1.x = __shfl_up_sync(0xffffffffu, p0.x, 1);
-            p1.y = __shfl_up_sync(0xffffffffu, p0.y, 1);
-            p2.x = __shfl_up_sync(0xffffffffu, p0.x, 2);
-            p2.y = __shfl_up_sync(0xffffffffu, p0.y, 2);
-            if (lane == 0) { p1 = P1; p2 = P2; }
-            if (lane == 1) { p2 = P1; }
-            float mu2 = mu, om2 = om;
-            long long ii2 = ii;
-            mm_update(prm, p0, p1, p2, mu2, om2, ii2);
-            long long dT = (ii2 - ii) * 4294967296LL + ((long long)(mu2 * MM_FIX) - (T & 0xffffffffLL));
-            long long dW = (long long)(om2 * MM_FIX) - Wf;
-            iT = dT;
-            iW = dW;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                long long a = __shfl_up_sync(0xffffffffu, iT, o);
-                long long b = __shfl_up_sync(0xffffffffu, iW, o);
-                if (lane >= o) { iT += a; iW += b; }
-            }
-            long long eT = __shfl_up_sync(0xffffffffu, iT, 1);
-            long long eW = __shfl_up_sync(0xffffffffu, iW, 1);
-            if (lane == 0) { eT = 0; eW = 0; }
-            const long long nT = Tb + eT, nW = Wb + eW;
-            const bool changed = (nT != T) || (nW != Wf);
-            T = nT;
-            Wf = nW;
-            if (!__any_sync(0xffffffffu, changed)) break;
-        }
-        windows++;
-        // accepted window: lane i holds the exact state before symbol i and its interpolant p0
-        const long long ii = T >> 32;
-        const bool computable = ii <= last_ok;
-        const bool inseg = ii < seg1;
-        const bool live = computable && inseg;
-        const unsigned live_mask = __ballot_sync(0xffffffffu, live);   // prefix of lanes (ii monotone)
-        const int nlive = (live_mask == 0xffffffffu) ? 32 : __ffs(~live_mask) - 1;
-        if (!have_entry) {
-            const unsigned ge = __ballot_sync(0xffffffffu, ii >= seg0 || !live);
-            if (ge) {
-                const int e = __ffs(ge) - 1;   // first lane at/after the segment start (or the stop lane)
-                // entry state = believed state of lane e with its two predecessors' interpolants
-                float2 q1, q2;
-                q1.x = __shfl_sync(0xffffffffu, p0.x, (e + 31) & 31);
-                q1.y = __shfl_sync(0xffffffffu, p0.y, (e + 31) & 31);
-                q2.x = __shfl_sync(0xffffffffu, p0.x, (e + 30) & 31);
-                q2.y = __shfl_sync(0xffffffffu, p0.y, (e + 30) & 31);
-                if (e == 0) { q1 = P1; q2 = P2; }
-                if (e == 1) { q2 = P1; }
-                if (lane == e) {
-                    MmState s;
-                    s.ii = ii;
-                    s.mu = (float)(unsigned int)(T & 0xffffffffLL) * MM_UNFIX;
-                    s.omega = (float)Wf * MM_UNFIX;
-                    s.p0 = q1;
-                    s.p1 = q2;
-                    entry[j] = s;
-                }
-                have_entry = true;
-            }
-        }
-        const bool emit = live && ii >= seg0;
-        const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
-        if (emit) {
-            const int pos = count + __popc(emit_mask & ((1u << lane) - 1));
-            if (pos < cap_seg) stage[pos] = p0;
-            else overflow = 1;
-        }
-        count += __popc(emit_mask);
-        if (nlive < 32) {
-            // stop lane: exact state before the first symbol this segment does not own
-            float2 q1, q2;
-            q1.x = __shfl_sync(0xffffffffu, p0.x, (nlive + 31) & 31);
-            q1.y = __shfl_sync(0xffffffffu, p0.y, (nlive + 31) & 31);
-            q2.x = __shfl_sync(0xffffffffu, p0.x, (nlive + 30) & 31);
-            q2.y = __shfl_sync(0xffffffffu, p0.y, (nlive + 30) & 31);
-            if (nlive == 0) { q1 = P1; q2 = P2; }
-            if (nlive == 1) { q2 = P1; }
-            if (lane == nlive) {
-                MmState s;
-                s.ii = ii;
-                s.mu = (float)(unsigned int)(T & 0xffffffffLL) * MM_UNFIX;
-                s.omega = (float)Wf * MM_UNFIX;
-                s.p0 = q1;
-                s.p1 = q2;
-                exit_[j] = s;
-            }
-            break;
-        }
-        // next window: base = state after lane 31
-        Tb = Tb + __shfl_sync(0xffffffffu, iT, 31);
-        Wb = Wb + __shfl_sync(0xffffffffu, iW, 31);
-        P2.x = __shfl_sync(0xffffffffu, p0.x, 30);
-        P2.y = __shfl_sync(0xffffffffu, p0.y, 30);
-        P1.x = __shfl_sync(0xffffffffu, p0.x, 31);
-        P1.y = __shfl_sync(0xffffffffu, p0.y, 31);
-    }
-    overflow = __any_sync(0xffffffffu, overflow);
-    if (lane == 0) {
-        MmSegOut so;
-        so.n_sym = count;
-        so.overflow = overflow;
-        so.iters = iters;
-        so.windows = windows;
-        segout[j] = so;
-    }
-}
-
 // ---------------------------------------------------------------------------------------
 // M&M as a CTA-wide sliding-window chain: one CTA per segment, NT lanes = NT consecutive symbols.
 //
@@ -839,7 +677,7 @@ mm_chain_kernel(const float2 *__restrict__ in /* index 0 = first new sample; MM_
                 float2 *__restrict__ stage, long long n, long long L, long long W, int nseg, long long cap_seg,
                 MmState *__restrict__ entry, MmState *__restrict__ exit_, const MmState *__restrict__ carried,
                 const unsigned char *__restrict__ redo, MmSegOut *__restrict__ segout, const float *__restrict__ table,
-                MmParams prm, int mode, long long in_ch_stride, long long stage_ch_stride, int R)
+                MmParams prm, int mode, long long in_ch_stride, long long stage_ch_stride, int R, int *__restrict__ stalled)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     float *s_tab = reinterpret_cast<float *>(s_raw);
@@ -905,8 +743,18 @@ mm_chain_kernel(const float2 *__restrict__ in /* index 0 = first new sample; MM_
         x_fill = target;
     }
 
+    // every iteration accepts at least one symbol, a symbol advances the base by at least one sample and the segment
+    // holds at most cap_seg symbols, so a finite stream needs fewer iterations than this; a non-finite sample stalls the
+    // loop itself (the advance becomes NaN), and the chain then stops here, reports overflow and raises *stalled (the
+    // host stops its re-run rounds on it)
+    const long long iter_cap = cap_seg + W + 1024;
     for (;;) {
         iters++;
+        if (iters > iter_cap) {
+            overflow = 1;
+            if (t == 0) atomicExch(stalled, 1);
+            break;
+        }
         cp_async_wait_all();
         __syncthreads();   // S0: ring visible, previous iteration's shared scratch consumed
         // ---- 1. interpolate at the believed state (skipped when (ii, k) did not move)
@@ -1097,7 +945,7 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
                   MmState *__restrict__ entry, MmState *__restrict__ exit_, const MmState *__restrict__ carried,
                   const unsigned char *__restrict__ redo, MmSegOut *__restrict__ segout, const float *__restrict__ table,
                   MmParams prm, int mode, long long in_ch_stride, long long stage_ch_stride, int R, MmCk *__restrict__ ckpt,
-                  int ncp, int C, MmTraj tr)
+                  int ncp, int C, MmTraj tr, int *__restrict__ stalled)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     float *s_tab = reinterpret_cast<float *>(s_raw);
@@ -1186,8 +1034,15 @@ mm_chain32_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, int
     int x_ready = x_fill;
     __syncthreads();
 
+    // iteration cap: see mm_chain_kernel (a non-finite sample stalls the loop; stop and report overflow)
+    const long long iter_cap = (long long)cap_seg + W + 1024;
     for (;;) {
         iters++;
+        if (iters > iter_cap) {
+            overflow = 1;
+            if (t == 0) atomicExch(stalled, 1);
+            break;
+        }
         float2 *sp = s_p + par * NT;
         // ---- 1. interpolate at the believed state (skipped when (ii, k) did not move)
         const float mu = (float)fr * MM_UNFIX;

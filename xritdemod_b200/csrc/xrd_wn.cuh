@@ -66,7 +66,8 @@ struct CostasWn {
         p -= T * rint(p * (0.5 / T) * 0.999999);   // whole turns towards zero-ish; |p| <= 2*pi afterwards for sane p
         p = (p > T) ? p - T : p;
         p = (p < -T) ? p + T : p;
-        f[0] = (p > T || p < -T || p != p) ? 0.0 : p;
+        // a NaN phase (non-finite input) stays NaN: that IS the literal loop's state from then on
+        f[0] = (p != p) ? p : ((p > T || p < -T) ? 0.0 : p);
         f[1] = fmin(fmax(f[1], -1.0), 1.0);
     }
     __device__ static __forceinline__ void extrapolate(const double *e, int r, double *o)

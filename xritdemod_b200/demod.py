@@ -20,13 +20,15 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIBXRD_PATH = os.path.join(_HERE, "libxrd.so")
 
-XRD_FLOATIQ, XRD_S16IQ, XRD_S8IQ = 0, 1, 2
-_NP_OF_TYPE = {XRD_FLOATIQ: np.float32, XRD_S16IQ: np.int16, XRD_S8IQ: np.int8}
+XRD_FLOATIQ, XRD_S16IQ, XRD_S8IQ, XRD_U8IQ, XRD_RTLU8IQ = 0, 1, 2, 3, 4
+_NP_OF_TYPE = {XRD_FLOATIQ: np.float32, XRD_S16IQ: np.int16, XRD_S8IQ: np.int8, XRD_U8IQ: np.uint8, XRD_RTLU8IQ: np.uint8}
 
 # every symbol include/xrd.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "xrd_config_defaults", "xrd_create", "xrd_destroy", "xrd_last_error", "xrd_add_samples", "xrd_process",
-    "xrd_demod_batch", "xrd_demod_batch_i8", "xrd_demod_device", "xrd_soft_i8", "xrd_get_state", "xrd_reset", "xrd_stream", "xrd_set_tuning", "xrd_get_stats",
+    "xrd_demod_batch", "xrd_demod_batch_i8", "xrd_demod_device", "xrd_soft_i8", "xrd_get_state", "xrd_set_state",
+    "xrd_checkpoint_size", "xrd_checkpoint_save", "xrd_checkpoint_load", "xrd_symbol_capacity", "xrd_reset", "xrd_stream",
+    "xrd_set_tuning", "xrd_get_stats",
     "xrd_design_rrc", "xrd_design_lowpass", "xrd_mmse_table", "xrd_costas_gains",
     "xrd_fir_create", "xrd_agc_create", "xrd_costas_create", "xrd_clock_recovery_create", "xrd_stage_work",
     "xrd_stage_set_tuning", "xrd_stage_set_loop_kernel", "xrd_stage_destroy", "xrd_stage_last_error", "xrd_device_check", "xrd_version",
@@ -61,7 +63,10 @@ class LoopState(C.Structure):
 class Tuning(C.Structure):
     _fields_ = [
         ("agc_seg", C.c_int32), ("agc_warm", C.c_int32), ("costas_seg", C.c_int32), ("costas_warm", C.c_int32),
-        ("mm_seg", C.c_int64), ("mm_warm", C.c_int64), ("mm_lanes", C.c_int32), ("loop_kernel", C.c_int32), ("h2d_pieces", C.c_int32), ("reserved", C.c_int32),
+        ("mm_seg", C.c_int64), ("mm_warm", C.c_int64), ("mm_lanes", C.c_int32), ("mm_kernel", C.c_int32),
+        ("mm_rerun", C.c_int32), ("mm_walk_lanes", C.c_int32), ("loop_kernel", C.c_int32), ("rerun_kernel", C.c_int32),
+        ("h2d_pieces", C.c_int32), ("h2d_piece_min_ki", C.c_int32), ("costas_chains_per_sm", C.c_int32),
+        ("agc_chains_per_sm", C.c_int32),
     ]
 
 
@@ -112,6 +117,13 @@ def lib():
     L.xrd_demod_device.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, i64p]
     L.xrd_soft_i8.argtypes = [vp, vp, C.c_size_t, vp]
     L.xrd_get_state.argtypes = [vp, C.c_int, C.POINTER(LoopState)]
+    L.xrd_set_state.argtypes = [vp, C.c_int, C.POINTER(LoopState)]
+    L.xrd_checkpoint_size.argtypes = [vp]
+    L.xrd_checkpoint_size.restype = C.c_size_t
+    L.xrd_checkpoint_save.argtypes = [vp, vp, C.c_size_t]
+    L.xrd_checkpoint_load.argtypes = [vp, vp, C.c_size_t]
+    L.xrd_symbol_capacity.argtypes = [vp, C.c_size_t]
+    L.xrd_symbol_capacity.restype = C.c_int64
     L.xrd_reset.argtypes = [vp]
     L.xrd_stream.argtypes = [vp]
     L.xrd_stream.restype = vp
@@ -335,8 +347,8 @@ class Demodulator:
         return float(np.float32(np.float32(self.cfg.sample_rate) / np.float32(D)) / np.float32(self.cfg.symbol_rate))
 
     def symbol_capacity(self, n_complex):
-        D = max(1, self.cfg.decimation)
-        return int(n_complex / D / max(1.0, np.floor(self.sps * 0.99 - 0.01))) + 64
+        """symbols one call over n_complex samples per channel can produce at most (xrd_symbol_capacity)"""
+        return int(self._check(lib().xrd_symbol_capacity(self._h, int(n_complex))))
 
     def set_tuning(self, **kw):
         t = Tuning()
@@ -353,6 +365,20 @@ class Demodulator:
         st = LoopState()
         self._check(lib().xrd_get_state(self._h, channel, C.byref(st)))
         return st
+
+    def set_state(self, st, channel=0):
+        """loop variables only (xrd_set_state); checkpoint()/restore() also carry the filter histories"""
+        self._check(lib().xrd_set_state(self._h, channel, C.byref(st)))
+
+    def checkpoint(self):
+        """bytes: loop variables, filter histories, M&M tail and totals of every channel (xrd_checkpoint_save)"""
+        n = lib().xrd_checkpoint_size(self._h)
+        buf = C.create_string_buffer(n)
+        self._check(lib().xrd_checkpoint_save(self._h, buf, n))
+        return buf.raw
+
+    def restore(self, blob):
+        self._check(lib().xrd_checkpoint_load(self._h, C.c_char_p(blob), len(blob)))
 
     def reset(self):
         self._check(lib().xrd_reset(self._h))

@@ -42,6 +42,16 @@ def build(force=False):
     return _SO
 
 
+def noise_only(seed, n, sigma=0.2):
+    """complex white noise, no signal: what the chain sees when the downlink drops out"""
+    rng = np.random.default_rng(seed)
+    out = np.empty(n, np.complex64)
+    for a in range(0, n, 1 << 22):
+        b = min(n, a + (1 << 22))
+        out[a:b] = (sigma * (rng.standard_normal(b - a) + 1j * rng.standard_normal(b - a))).astype(np.complex64)
+    return out
+
+
 def _lib():
     global _LIB
     if _LIB is None:
@@ -50,6 +60,8 @@ def _lib():
         L.xrd_siggen_bits.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]
         L.xrd_cf32_to_s16.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.xrd_cf32_to_s8.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.xrd_cf32_to_u8.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.xrd_siggen_set_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -111,6 +123,18 @@ def to_s16(x):
     x = np.ascontiguousarray(x, np.complex64)
     out = np.empty(2 * len(x), np.int16)
     _lib().xrd_cf32_to_s16(x.ctypes.data_as(C.c_void_p), len(x), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def set_threads(n):
+    """worker threads of generate(); launchers like torchrun export OMP_NUM_THREADS=1"""
+    _lib().xrd_siggen_set_threads(int(n))
+
+
+def to_u8(x):
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.empty(2 * len(x), np.uint8)
+    _lib().xrd_cf32_to_u8(x.ctypes.data_as(C.c_void_p), len(x), out.ctypes.data_as(C.c_void_p))
     return out
 
 
