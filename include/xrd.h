@@ -150,6 +150,25 @@ int xrd_checkpoint_load(xrd_demod *d, const void *blob, size_t bytes);
  * relative limit and gain_mu exactly as the M&M stage sizes its own staging. */
 int64_t xrd_symbol_capacity(const xrd_demod *d, size_t n_complex);
 
+/* Diagnostics of the last chain call on one channel, produced on the device by the pass that writes the symbols.
+ *   frame / n_frame  what processSamples() hands to DiagManager::addSamples after every chunk -- the first
+ *                    min(symbols, 1024) FLOATS of the interleaved complex symbol buffer (demodulator.cpp:161-163) --
+ *                    in the int8 form DiagManager puts on its UDP socket: v * 128, clamp [-128, 127], C cast
+ *                    (DiagManager.cpp:31-47).  A caller sends `frame` as is once 1024 bytes have accumulated.
+ *   mean_*           E|I|, E[I^2], E[Q^2] over all symbols of the call
+ *   snr_db           10 log10(E|I|^2 / (E[I^2] - E|I|^2)): signal to noise on the decision axis (the reference's
+ *                    GNU Radio prototype displays an RMS-ratio SNR, demod_tcp_qt.py:263-298; the C++ program none)
+ *   lock             E[I^2] / (E[I^2] + E[Q^2]): -> 1 when the Costas loop holds the BPSK constellation on I,
+ *                    0.5 without carrier lock */
+typedef struct {
+    int32_t n_frame;
+    int8_t frame[1024];
+    uint64_t n_symbols;
+    double mean_abs_i, mean_sq_i, mean_sq_q;
+    float snr_db, lock;
+} xrd_diag;
+int xrd_get_diag(xrd_demod *d, int channel, xrd_diag *out);
+
 /* Back to the just-created state (loop states, filter histories, queued samples, totals):
  * what deleting and re-constructing the five operators does in the reference
  * (demodulator.cpp:446-450, 503-523), without giving device buffers back. */
@@ -178,6 +197,9 @@ typedef struct {
     int32_t h2d_pieces;                /* host-input calls: copy/compute pieces, 1..16 (default 2) */
     int32_t h2d_piece_min_ki;          /* minimum piece, Ki samples (default 16 M samples) */
     int32_t costas_chains_per_sm, agc_chains_per_sm;   /* segments per SM of the first pass (defaults 8, 16) */
+    int32_t agc_kernel;                /* AGC first pass only, overriding loop_kernel (same values) */
+    int32_t chase;                     /* 1 (default): a certified AGC/Costas re-run that has not merged at the end of
+                                          its segment continues into the next one; 2: stops there (one more round) */
 } xrd_tuning;
 int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t);
 

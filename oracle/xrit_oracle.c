@@ -798,3 +798,15 @@ void xo_convert_rtl_u8(const uint8_t *in, int64_t n_complex, float alpha, float 
     }
     *avg = iavg;
 }
+
+/* DiagManager::threadLoop (DiagManager.cpp:35-42): val * 128, clamp to [-128, 127], static_cast<char> */
+void xo_diag_i8(const float *v, int64_t n, int8_t *out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        float val = v[i];
+        val *= 128.f;
+        val = val > 127 ? 127 : val;
+        val = val < -128 ? -128 : val;
+        out[i] = (int8_t)(val);
+    }
+}

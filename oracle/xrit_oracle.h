@@ -116,6 +116,8 @@ float xo_chain_sps(const xo_chain *c);
 
 /* SymbolManager int8 rule (SymbolManager.cpp:43-46): Re(s)*127, clamp, C cast */
 void xo_soft_i8(const float *sym_cf32, int64_t n, int8_t *out);
+/* DiagManager's int8 rule (DiagManager.cpp:35-42) for the floats of the diagnostic tap (demodulator.cpp:161-163) */
+void xo_diag_i8(const float *v, int64_t n, int8_t *out);
 /* onSamplesAvailable conversions (demodulator.cpp:57-70) */
 void xo_convert_s16(const int16_t *in, int64_t n_complex, float *out);
 void xo_convert_s8(const int8_t *in, int64_t n_complex, float *out);

@@ -116,6 +116,7 @@ def lib():
     L.xo_soft_i8.argtypes = [vp, C.c_int64, vp]
     L.xo_convert_s16.argtypes = [vp, C.c_int64, vp]
     L.xo_convert_s8.argtypes = [vp, C.c_int64, vp]
+    L.xo_diag_i8.argtypes = [vp, C.c_int64, vp]
     L.xo_convert_u8.argtypes = [vp, C.c_int64, vp]
     L.xo_rtl_alpha.argtypes = [C.c_uint32]
     L.xo_rtl_alpha.restype = C.c_float
@@ -319,6 +320,13 @@ def convert_s8(x):
     out = np.empty(len(x), np.float32)
     lib().xo_convert_s8(_p(x), len(x) // 2, _p(out))
     return out.view(np.complex64)
+
+
+def diag_i8(floats):
+    v = np.ascontiguousarray(floats, np.float32).reshape(-1)
+    out = np.empty(len(v), np.int8)
+    lib().xo_diag_i8(_p(v), len(v), _p(out))
+    return out
 
 
 def convert_u8(x):

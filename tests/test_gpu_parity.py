@@ -424,6 +424,36 @@ def test_u8_ingest_formats(gpu, xrd, oracle, siggen):
         xrd.Demodulator(mode="hrit").demod(raw, type=xrd.XRD_RTLU8IQ)   # serial DC blocker: FIFO seam only
 
 
+def test_diag_tap_and_signal_estimates(gpu, xrd, oracle):
+    """xrd_get_diag: the DiagManager frame of the last call (first min(symbols, 1024) floats of the symbol buffer,
+    demodulator.cpp:161-163, as the int8 bytes of DiagManager.cpp:35-42) bit for bit, and the SNR / lock estimates
+    against numpy on the oracle's symbols"""
+    _, x0 = make_signal("hrit", 1 << 20)
+    _, x1 = make_signal("hrit", 1 << 20, channel=1, esn0_db=6.0)
+    d = xrd.Demodulator(mode="hrit", n_channels=2)
+    ch = [oracle.Chain(oracle.config(True)), oracle.Chain(oracle.config(True))]
+    for lo, hi in [(0, 700), (700, 700 + 300000), (300700, 1 << 20)]:     # a chunk with < 512 symbols, then long ones
+        d.demod(np.stack([x0[lo:hi], x1[lo:hi]]))
+        for c, xc in enumerate((x0, x1)):
+            ref = ch[c].process(xc[lo:hi])
+            g = d.diag(c)
+            nf = min(len(ref), 1024)
+            assert g.n_frame == nf and g.n_symbols == len(ref)
+            np.testing.assert_array_equal(np.frombuffer(bytes(g.frame), np.int8)[:nf], oracle.diag_i8(ref.view(np.float32)[:nf]))
+            if len(ref) > 1000:
+                re, im = ref.real.astype(np.float64), ref.imag.astype(np.float64)
+                m1, m2, q2 = np.abs(re).mean(), (re * re).mean(), (im * im).mean()
+                assert abs(g.mean_abs_i - m1) < 1e-9 and abs(g.mean_sq_i - m2) < 1e-9 and abs(g.mean_sq_q - q2) < 1e-9
+                assert abs(g.snr_db - 10 * np.log10(m1 * m1 / (m2 - m1 * m1))) < 1e-3
+                assert abs(g.lock - m2 / (m2 + q2)) < 1e-6
+    locked, noisy = d.diag(0), d.diag(1)
+    assert locked.lock > 0.9 and locked.snr_db > noisy.snr_db + 3.0     # Es/N0 12 dB against 6 dB
+    z = xrd.Demodulator(mode="hrit")
+    rng = np.random.default_rng(1)
+    z.demod((0.2 * (rng.standard_normal(200000) + 1j * rng.standard_normal(200000))).astype(np.complex64))
+    assert 0.35 < z.diag().lock < 0.65                                   # no carrier: power splits between I and Q
+
+
 def test_reset_and_state(gpu, xrd, oracle):
     _, x = make_signal("hrit", 300000)
     ref = oracle.Chain(oracle.config(True)).process(x)

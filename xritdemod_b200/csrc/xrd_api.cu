@@ -4,6 +4,7 @@
 #include "../../include/xrd.h"
 #include "xrd_kernels.cuh"
 #include "xrd_wn.cuh"
+#include "xrd_fir_tma.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -57,7 +58,8 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         bytes = 0;
-        size_t want = need + need / 8 + 256;
+        // whole 1 KB rows: the TMA tensor map of a sample buffer (xrd_fir_tma.cuh) covers the allocation exactly
+        size_t want = (need + need / 8 + 256 + 1023) & ~(size_t)1023;
         XRD_CUDA(cudaMalloc(&p, want));
         bytes = want;
     }
@@ -220,13 +222,50 @@ struct FirStage {
         XRD_CUDA(cudaMemcpy(d_taps.p, taps, sizeof(float) * n, cudaMemcpyHostToDevice));
     }
     int hist() const { return ntaps - 1; }
-    // in: x[0] of this call (history before it); n_out outputs per channel
+    // TMA path of the stride-1 filter: tensor map of the allocation the input lives in, re-encoded when it moves
+    bool use_tma = true;
+    CUtensorMap tmap;
+    const void *tmap_base = nullptr;
+    size_t tmap_bytes = 0;
+    int tma_ctas_per_sm = 0, sm_count = 0;
+    bool run_tma(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n_out, int nch, long long in_stride,
+                 long long out_stride, const DevBuf *src)
+    {
+        if (!use_tma || !src || !src->p || ft_rows(ntaps) > 256) return false;
+        const size_t smem = ft_smem_bytes(ntaps);
+        if (smem > 200 * 1024) return false;
+        const float2 *base = src->as<float2>();
+        if (in - (ntaps - 1) < base || n_out > (1LL << 40)) return false;
+        if (tmap_base != src->p || tmap_bytes != src->bytes) {
+            if (!ft_make_map(&tmap, src->p, src->bytes, ntaps)) return false;
+            tmap_base = src->p;
+            tmap_bytes = src->bytes;
+        }
+        if (!tma_ctas_per_sm) {
+            XRD_CUDA(cudaFuncSetAttribute(fir_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int dev = 0;
+            XRD_CUDA(cudaGetDevice(&dev));
+            XRD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+            XRD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tma_ctas_per_sm, fir_tma_kernel, FT_THREADS, smem));
+            if (tma_ctas_per_sm < 1) tma_ctas_per_sm = 1;
+        }
+        const long long tiles_per_ch = (n_out + FT_TILE - 1) / FT_TILE;
+        const long long n_tiles = tiles_per_ch * nch;
+        if (n_tiles > 0x7fffffffLL) return false;
+        const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * tma_ctas_per_sm);
+        XRD_LAUNCH(c, fir_tma_kernel, grid, FT_THREADS, smem, st, tmap, out, d_taps.as<float>(), ntaps, n_out,
+                   (long long)(in - base), in_stride, out_stride, (int)tiles_per_ch, (int)n_tiles);
+        return true;
+    }
+    // in: x[0] of this call (history before it); n_out outputs per channel.  src: the allocation `in` points into
+    // (enables the TMA-staged kernel for decimation 1)
     void run(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n_out, int nch, long long in_stride,
-             long long out_stride)
+             long long out_stride, const DevBuf *src = nullptr)
     {
         if (n_out <= 0) return;
         const int tp = (ntaps + 1) & ~1;
         if (D == 1) {
+            if (run_tma(c, st, in, out, n_out, nch, in_stride, out_stride, src)) return;
             const size_t smem = sizeof(float) * tp + sizeof(float2) * (1 + FIR_TILE + ntaps - 1);
             if (smem > 48 * 1024)
                 XRD_CUDA(cudaFuncSetAttribute(fir1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -307,6 +346,7 @@ template <class LOOP> struct SegStage {
     int wn_variant = 2;   // 2: one warp per chain (K = 4); 3..7: one CTA per chain, (K, warps) = (1,4) (2,4) (1,2) (2,2) (2,8)
     int redo_variant = 4; // kernel of the certified re-runs: few chains, so the widest window (fastest single chain) wins
     bool use_mirror = false;
+    bool chase = true;        // CTA-chain re-runs that do not merge inside their segment keep going into the next one
     int nch = 1, sm_count = 148;
     DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list, d_ckpt, d_iters, d_psi, d_adv, d_pre, d_adv0;
     int pre_len = 0;          // Costas: samples of segment 0 run ahead of the branch resolution (0: none)
@@ -369,7 +409,8 @@ template <class LOOP> struct SegStage {
 #define XRD_WN_CTA(KV, WV)                                                                                              \
     XRD_LAUNCH(c, (wn_cta_kernel<LOOP, KV, WV>), n_work, 32 * WV, 0, st, in, out, n, Ls, Ws, nseg, n_work,              \
                d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(), d_ckpt.as<State>(), ncp, \
-               WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride, hist)
+               WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride, hist,                        \
+               (mode == 1 && chase) ? d_redo.as<unsigned char>() : (const unsigned char *)nullptr)
             if (variant == 3) XRD_WN_CTA(1, 4);
             else if (variant == 4) XRD_WN_CTA(2, 4);
             else if (variant == 5) XRD_WN_CTA(1, 2);
@@ -531,6 +572,8 @@ struct MmStage {
     int *h_nredo = nullptr;
     signed char *out_i8 = nullptr;  // when set, the compaction also (out != null) or only (out == null) emits int8 soft symbols
     std::vector<long long> h_offsets;
+    DevBuf d_diag;                  // per-channel diagnostics of the last call (MmDiag), filled by the compaction pass
+    std::vector<MmDiag> h_diag;
     uint64_t rounds = 0, redone = 0, windows = 0, iters = 0;
 
     MmState s_init;
@@ -558,6 +601,7 @@ struct MmStage {
         d_nredo.ensure(4 * sizeof(int));   // [0] segments flagged by the verify pass, [1] delta re-runs that gave up,
                                            // [2] a chain hit its iteration cap (non-finite samples stalled the loop)
         d_overflow.ensure(sizeof(int));
+        d_diag.ensure(sizeof(MmDiag) * nch);
         if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, 4 * sizeof(int)));
         int dev = 0;
         XRD_CUDA(cudaGetDevice(&dev));
@@ -718,12 +762,14 @@ struct MmStage {
             launch_chain(c, st, grid, in, n, Ls, nseg, cap_seg, 1, in_stride, stage_stride);
         }
         XRD_CUDA(cudaMemsetAsync(d_overflow.p, 0, sizeof(int), st));
+        XRD_CUDA(cudaMemsetAsync(d_diag.p, 0, sizeof(MmDiag) * nch, st));
         XRD_LAUNCH(c, mm_offsets_kernel, nch, 32, 0, st, nseg, d_segout.as<MmSegOut>(), d_offsets.as<long long>(),
-                   d_overflow.as<int>());
+                   d_overflow.as<int>(), d_diag.as<MmDiag>());
         const int parts = std::max(1, std::min(64, (sm_count * 16) / std::max(1, nseg * nch)));
         dim3 cg((unsigned)nseg * parts, nch);
         XRD_LAUNCH(c, mm_compact_kernel, cg, 256, 0, st, d_stage.as<float2>(), out, nseg, cap_seg,
-                   d_segout.as<MmSegOut>(), d_offsets.as<long long>(), out_cap, stage_stride, out_stride, out_i8);
+                   d_segout.as<MmSegOut>(), d_offsets.as<long long>(), out_cap, stage_stride, out_stride, out_i8,
+                   d_diag.as<MmDiag>());
         XRD_LAUNCH(c, mm_rebase_kernel, (nch + 127) / 128, 128, 0, st, d_carried.as<MmState>(), d_exit.as<MmState>(),
                    nseg, nch, n);
         h_offsets.resize((size_t)(nseg + 1) * nch);
@@ -731,6 +777,8 @@ struct MmStage {
         XRD_CUDA(cudaMemcpyAsync(h_offsets.data(), d_offsets.p, sizeof(long long) * h_offsets.size(),
                                  cudaMemcpyDeviceToHost, st));
         XRD_CUDA(cudaMemcpyAsync(so.data(), d_segout.p, sizeof(MmSegOut) * tot, cudaMemcpyDeviceToHost, st));
+        h_diag.resize(nch);
+        XRD_CUDA(cudaMemcpyAsync(h_diag.data(), d_diag.p, sizeof(MmDiag) * nch, cudaMemcpyDeviceToHost, st));
         XRD_CUDA(cudaMemcpyAsync(h_nredo + 1, d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         XRD_CUDA(cudaMemcpyAsync(h_nredo + 2, d_nredo.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         XRD_CUDA(cudaStreamSynchronize(st));
@@ -939,7 +987,7 @@ struct xrd_demod {
         t_agc.stop(stream);
         t_rrc.start(stream);
         // (when D == 1 and the input was converted into b_rrc, AGC has consumed it by now)
-        rrc.run(ctr, stream, agc_out, b_rrc.as<float2>() + nd_off, nd, nch, agc_stride(), nd_cap());
+        rrc.run(ctr, stream, agc_out, b_rrc.as<float2>() + nd_off, nd, nch, agc_stride(), nd_cap(), &b_agc);
         t_rrc.stop(stream);
         float2 *cos_out = b_cos.as<float2>() + MM_TAIL + nd_off;
         t_cos.start(stream);
@@ -1557,6 +1605,27 @@ int xrd_checkpoint_load(xrd_demod *d, const void *blob, size_t bytes)
     });
 }
 
+int xrd_get_diag(xrd_demod *d, int channel, xrd_diag *out)
+{
+    if (!d || !out || channel < 0 || channel >= d->nch) return XRD_E_ARG;
+    memset(out, 0, sizeof *out);
+    if ((int)d->mm.h_diag.size() <= channel) return XRD_OK;   // no call yet
+    const MmDiag &g = d->mm.h_diag[channel];
+    out->n_frame = g.n_frame;
+    memcpy(out->frame, g.frame, sizeof out->frame);
+    out->n_symbols = g.n;
+    if (g.n) {
+        const double m1 = g.sum_abs_i / (double)g.n, m2 = g.sum_sq_i / (double)g.n, q2 = g.sum_sq_q / (double)g.n;
+        out->mean_abs_i = m1;
+        out->mean_sq_i = m2;
+        out->mean_sq_q = q2;
+        const double noise = m2 - m1 * m1;
+        out->snr_db = (noise > 0 && m1 > 0) ? (float)(10.0 * log10(m1 * m1 / noise)) : 0.f;
+        out->lock = (m2 + q2 > 0) ? (float)(m2 / (m2 + q2)) : 0.f;
+    }
+    return XRD_OK;
+}
+
 int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
 {
     if (!d || !t) return XRD_E_ARG;
@@ -1582,6 +1651,13 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
         d->agc.redo_variant = d->costas.redo_variant = t->loop_kernel;   // unless rerun_kernel says otherwise below
     }
     if (t->rerun_kernel) d->agc.redo_variant = d->costas.redo_variant = t->rerun_kernel;
+    if (t->agc_kernel < 0 || t->agc_kernel > 7) return XRD_E_ARG;
+    if (t->agc_kernel == 1) d->agc.use_wn = false;
+    else if (t->agc_kernel) {
+        d->agc.use_wn = agc_wn_ok(d->agc.prm.max_gain);
+        d->agc.wn_variant = t->agc_kernel;
+    }
+    if (t->chase) d->agc.chase = d->costas.chase = (t->chase == 1);
     if (t->costas_chains_per_sm) d->costas.chains_per_sm = t->costas_chains_per_sm;
     if (t->agc_chains_per_sm) d->agc.chains_per_sm = t->agc_chains_per_sm;
     if (t->mm_seg) d->mm.L = std::max<long long>(t->mm_seg, 64);
@@ -1792,7 +1868,7 @@ int xrd_stage_work(xrd_stage *s, const float *in, float *out, int length)
         long long n_copy = n_out;
         switch (s->kind) {
         case xrd_stage::FIR:
-            s->fir.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_out, 1, 0, 0);
+            s->fir.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_out, 1, 0, 0, &s->b_in);
             break;
         case xrd_stage::AGC:
             s->agc.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_in, 0, 0);

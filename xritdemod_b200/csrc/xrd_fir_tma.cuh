@@ -1,0 +1,219 @@
+// xrd_fir_tma.cuh -- the stride-1 FIR (FirFilter::Work with decimation 1: the RRC matched filter,
+// reference demodulator.cpp:148,450) as a persistent kernel whose input tiles are staged by the
+// TMA unit (cp.async.bulk.tensor, UTMALDG in SASS) into a double-buffered shared-memory ring
+// guarded by mbarriers.
+//
+// The sample buffer is described to the TMA as a 2-D tensor of floats, 256 floats (128 cf32
+// samples, 1 KB) per row; a tile of FT_TILE outputs needs the FT_TILE + ntaps - 1 samples that
+// end at its last output, i.e. at most ft_rows(ntaps) whole rows starting at the row that holds
+// its first history sample.  One elected thread per CTA arms the stage's mbarrier with the byte
+// count and issues ONE bulk tensor copy per tile; the 256 threads then run the same register
+// sliding window as fir1_kernel out of shared memory (thread t owns 9 consecutive outputs; I and
+// Q accumulate in one packed FFMA2, taps k = 0..T-1 by fmaf from zero -- the oracle's order, so
+// the result is bit-identical).  Rows past the end of the allocation are zero-filled by the TMA
+// and only ever feed outputs that are not stored.
+//
+// Persistent: grid = CTAs resident on the device; CTA b takes tiles b, b + grid, b + 2 grid, ...
+// (of all channels), taps are loaded once per CTA, and the copy of tile i + 2 is in flight while
+// tiles i and i + 1 are computed.
+#pragma once
+#include <cuda.h>
+
+#include "xrd_kernels.cuh"
+
+namespace xrd {
+
+constexpr int FT_THREADS = 256;
+constexpr int FT_R = 9;                      // outputs per thread (odd: conflict-free 8-byte shared loads)
+constexpr int FT_TILE = FT_THREADS * FT_R;   // outputs per tile
+constexpr int FT_ROW = 128;                  // samples per tensor row (1 KB)
+constexpr int FT_STAGES = 2;
+constexpr int FT_HEAD = 128;                 // bytes before the first stage: two mbarriers, and slot -1 of stage 0
+
+__host__ __device__ inline int ft_rows(int ntaps)
+{
+    // a tile starts up to FT_ROW - 1 samples into its first row and spans FT_TILE + ntaps - 1 samples
+    return (FT_ROW - 1 + FT_TILE + ntaps - 1 + FT_ROW - 1) / FT_ROW;
+}
+__host__ __device__ inline size_t ft_smem_bytes(int ntaps)
+{
+    return FT_HEAD + (size_t)FT_STAGES * ft_rows(ntaps) * FT_ROW * sizeof(float2) + sizeof(float) * (size_t)((ntaps + 3) & ~3);
+}
+
+__device__ __forceinline__ void ft_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void ft_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    // bounded: a copy that never completes (a bad tensor map) must end in a launch failure, not in a hung device
+    for (unsigned spins = 0;; spins++) {
+        unsigned done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins > (1u << 24)) __trap();
+    }
+}
+// one bulk tensor copy: the box of `tmap` at (column 0, row) -> shared memory, completion counted on `bar`
+__device__ __forceinline__ void ft_tma_load_rows(void *smem_dst, const CUtensorMap *tmap, int row, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(tmap), "r"(0), "r"(row), "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+
+__global__ void __launch_bounds__(FT_THREADS)
+fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, float2 *__restrict__ out, const float *__restrict__ taps, int ntaps,
+               long long n_out, long long in_off /* samples from the tensor base to x[0] of channel 0 */,
+               long long in_ch_stride, long long out_ch_stride, int tiles_per_ch, int n_tiles)
+{
+    extern __shared__ __align__(128) unsigned char ft_smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ft_smem);
+    const int H = ntaps - 1;
+    const int rows = ft_rows(ntaps);
+    const int stage_elems = rows * FT_ROW;
+    float2 *buf0 = reinterpret_cast<float2 *>(ft_smem + FT_HEAD);
+    float *s_taps = reinterpret_cast<float *>(ft_smem + FT_HEAD + (size_t)FT_STAGES * stage_elems * sizeof(float2));
+    const int tid = threadIdx.x;
+    for (int i = tid; i < ntaps; i += FT_THREADS) s_taps[i] = taps[i];
+    if (tid == 0) {
+        ft_mbar_init(&bar[0], 1);
+        ft_mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    // first sample a tile needs, relative to the tensor base
+    auto tile_origin = [&](int tile, int &ch, long long &tile0) -> long long {
+        ch = tile / tiles_per_ch;
+        tile0 = (long long)(tile - ch * tiles_per_ch) * FT_TILE;
+        return in_off + (long long)ch * in_ch_stride + tile0 - H;
+    };
+    auto issue = [&](int tile, int s) {
+        int ch;
+        long long tile0;
+        const long long g0 = tile_origin(tile, ch, tile0);
+        ft_mbar_expect_tx(&bar[s], (unsigned)(stage_elems * sizeof(float2)));
+        ft_tma_load_rows(buf0 + (size_t)s * stage_elems, &tmap, (int)(g0 / FT_ROW), &bar[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < FT_STAGES; s++) {
+            const int tile = blockIdx.x + s * gridDim.x;
+            if (tile < n_tiles) issue(tile, s);
+        }
+    }
+    const int o0 = tid * FT_R;   // first output of this thread (tile-relative)
+    for (int it = 0;; it++) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        if (tile >= n_tiles) break;
+        const int s = it & 1;
+        int ch;
+        long long tile0;
+        const long long g0 = tile_origin(tile, ch, tile0);
+        const int shift = (int)(g0 % FT_ROW);
+        const int tile_n = (int)min((long long)FT_TILE, n_out - tile0);
+        ft_mbar_wait(&bar[s], (unsigned)((it >> 1) & 1));
+        if (o0 < tile_n) {
+            // s_x[i] = x[tile0 - H + i]
+            const float2 *s_x = buf0 + (size_t)s * stage_elems + shift;
+            float2 w[FT_R], acc[FT_R];
+#pragma unroll
+            for (int r = 0; r < FT_R; r++) {
+                const int m = o0 + r;
+                w[r] = (m < tile_n) ? s_x[m + H] : make_float2(0.f, 0.f);
+                acc[r] = make_float2(0.f, 0.f);
+            }
+            const float2 *xb = s_x + o0 + H;   // xb[-k-1] = next sample entering the window
+            int kb = 0;
+            for (; kb + FT_R <= ntaps; kb += FT_R) {
+#pragma unroll
+                for (int q = 0; q < FT_R; q++) {
+                    const float h = s_taps[kb + q];
+                    const float2 h2 = make_float2(h, h);
+#pragma unroll
+                    for (int r = 0; r < FT_R; r++) {
+                        const int sl = (r - q + FT_R) % FT_R;
+                        acc[r] = __ffma2_rn(h2, w[sl], acc[r]);   // two IEEE fmaf in one FFMA2 (I and Q share the tap)
+                    }
+                    // relative index -(k+1) enters the slot that (R-1-k) leaves (the last one reads slot -1: unused)
+                    w[(FT_R - 1 - q) % FT_R] = xb[-(kb + q) - 1];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < FT_R; q++) {
+                if (kb + q < ntaps) {
+                    const float h = s_taps[kb + q];
+                    const float2 h2 = make_float2(h, h);
+#pragma unroll
+                    for (int r = 0; r < FT_R; r++) {
+                        const int sl = (r - q + FT_R) % FT_R;
+                        acc[r] = __ffma2_rn(h2, w[sl], acc[r]);
+                    }
+                    w[(FT_R - 1 - q) % FT_R] = xb[-(kb + q) - 1];
+                }
+            }
+            float2 *o = out + (size_t)ch * out_ch_stride + tile0 + o0;
+#pragma unroll
+            for (int r = 0; r < FT_R; r++)
+                if (o0 + r < tile_n) o[r] = acc[r];
+        }
+        __syncthreads();   // every thread is done reading this stage: its buffer may be overwritten
+        if (tid == 0) {
+            const int nt = tile + FT_STAGES * gridDim.x;
+            if (nt < n_tiles) issue(nt, s);
+        }
+    }
+}
+
+// ---- host side: the tensor map of a sample buffer (cuTensorMapEncodeTiled through the runtime's driver entry point,
+// so that libxrd.so does not link libcuda) ----
+typedef CUresult (*ft_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline ft_encode_fn ft_encoder()
+{
+    static ft_encode_fn fn = []() -> ft_encode_fn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<ft_encode_fn>(p);
+    }();
+    return fn;
+}
+
+// base: start of the allocation (cudaMalloc: 256-byte aligned), bytes: its size.  false: no TMA path (caller falls back)
+inline bool ft_make_map(CUtensorMap *map, void *base, size_t bytes, int ntaps)
+{
+    ft_encode_fn enc = ft_encoder();
+    if (!enc || !base || (reinterpret_cast<unsigned long long>(base) & 15)) return false;
+    const cuuint64_t rows = (cuuint64_t)(bytes / (FT_ROW * sizeof(float2)));   // whole rows only
+    if (rows == 0 || rows > 0xffffffffull) return false;
+    const cuuint64_t dims[2] = {2 * FT_ROW, rows};
+    const cuuint64_t strides[1] = {FT_ROW * sizeof(float2)};
+    const cuuint32_t box[2] = {2 * FT_ROW, (cuuint32_t)ft_rows(ntaps)};
+    const cuuint32_t estr[2] = {1, 1};
+    if (box[1] > 256) return false;
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace xrd

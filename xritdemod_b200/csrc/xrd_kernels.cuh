@@ -1613,11 +1613,34 @@ __device__ __forceinline__ signed char soft_i8(float re)
     return (signed char)(int)f;
 }
 
+// DiagManager's byte rule (DiagManager.cpp:37-41): val * 128, clamp to [-128, 127], C cast
+__device__ __forceinline__ signed char diag_i8(float v)
+{
+    float f = v * 128.f;
+    f = f > 127.f ? 127.f : f;
+    f = f < -128.f ? -128.f : f;
+    return (signed char)(int)f;
+}
+
+// Per-channel diagnostics of one call, produced by the compaction pass (it touches every symbol anyway):
+//  * frame: what the reference hands to DiagManager::addSamples after every chunk -- the first min(symbols, 1024)
+//    FLOATS of the interleaved complex symbol buffer (demodulator.cpp:161-163) -- already in the int8 form
+//    DiagManager's thread puts on its UDP socket (DiagManager.cpp:31-47);
+//  * sums over all symbols of the call for a lock / SNR estimate (the reference's GNU Radio prototype shows an
+//    RMS-ratio SNR, demod_tcp_qt.py:263-298; the C++ demodulator has none).
+struct MmDiag {
+    double sum_abs_i, sum_sq_i, sum_sq_q;
+    unsigned long long n;
+    int n_frame;
+    int pad;
+    signed char frame[1024];
+};
+
 // gather the per-segment staging slots into the contiguous symbol stream (cf32 and / or int8 soft symbols)
 __global__ void mm_compact_kernel(const float2 *__restrict__ stage, float2 *__restrict__ out, int nseg, long long cap_seg,
                                   const MmSegOut *__restrict__ segout, long long *__restrict__ offsets /* [nseg+1] */,
                                   long long out_cap, long long stage_ch_stride, long long out_ch_stride,
-                                  signed char *__restrict__ out_i8)
+                                  signed char *__restrict__ out_i8, MmDiag *__restrict__ diag)
 {
     const int ch = blockIdx.y;
     stage += (size_t)ch * stage_ch_stride;
@@ -1632,16 +1655,43 @@ __global__ void mm_compact_kernel(const float2 *__restrict__ stage, float2 *__re
     const long long o = offsets[j];
     const int c = segout[j].n_sym;
     const float2 *src = stage + (size_t)j * cap_seg;
+    double s_abs = 0.0, s_i = 0.0, s_q = 0.0;
+    unsigned cnt = 0;
     for (long long i = (long long)part * blockDim.x + threadIdx.x; i < c; i += (long long)parts * blockDim.x)
         if (o + i < out_cap) {
             const float2 v = src[i];
             if (out) out[o + i] = v;
             if (out_i8) out_i8[o + i] = soft_i8(v.x);   // the byte SymbolManager::process sends (SymbolManager.cpp:43-46)
+            if (diag) {
+                s_abs += (double)fabsf(v.x);
+                s_i += (double)v.x * (double)v.x;
+                s_q += (double)v.y * (double)v.y;
+                cnt++;
+                if (o + i < 512) {
+                    diag[ch].frame[2 * (o + i)] = diag_i8(v.x);
+                    diag[ch].frame[2 * (o + i) + 1] = diag_i8(v.y);
+                }
+            }
         }
+    if (diag) {
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) {
+            s_abs += __shfl_xor_sync(0xffffffffu, s_abs, w);
+            s_i += __shfl_xor_sync(0xffffffffu, s_i, w);
+            s_q += __shfl_xor_sync(0xffffffffu, s_q, w);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, w);
+        }
+        if ((threadIdx.x & 31) == 0 && cnt) {
+            atomicAdd(&diag[ch].sum_abs_i, s_abs);
+            atomicAdd(&diag[ch].sum_sq_i, s_i);
+            atomicAdd(&diag[ch].sum_sq_q, s_q);
+            atomicAdd(&diag[ch].n, (unsigned long long)cnt);
+        }
+    }
 }
 
 __global__ void mm_offsets_kernel(int nseg, const MmSegOut *__restrict__ segout, long long *__restrict__ offsets,
-                                  int *__restrict__ overflow)
+                                  int *__restrict__ overflow, MmDiag *__restrict__ diag)
 {
     const int ch = blockIdx.x;
     segout += (size_t)ch * nseg;
@@ -1655,6 +1705,7 @@ __global__ void mm_offsets_kernel(int nseg, const MmSegOut *__restrict__ segout,
             ov |= segout[j].overflow;
         }
         offsets[nseg] = o;
+        if (diag) diag[ch].n_frame = (int)(o < 1024 ? o : 1024);   // demodulator.cpp:162: symbols < 1024 ? symbols : 1024 floats
         if (ov) atomicExch(overflow, 1);
     }
 }

@@ -646,7 +646,8 @@ wn_cta_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long
               typename LOOP::State *__restrict__ entry, typename LOOP::State *__restrict__ exit_,
               const typename LOOP::State *__restrict__ carried, const int *__restrict__ list,
               typename LOOP::State *__restrict__ ckpt, int ncp, int C, unsigned long long *__restrict__ iters_total,
-              typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride, long long hist)
+              typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride, long long hist,
+              const unsigned char *__restrict__ redo)
 {
     typedef typename LOOP::State State;
     __shared__ __align__(16) typename WnCta<LOOP, K, WPC>::Shared sh;
@@ -686,7 +687,28 @@ wn_cta_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long
         st = entry[g];
         bool merged = false;
         st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE>(x, y, 0, len, st, prm, sh, ck, C, &merged, &iters);
-        if (threadIdx.x == 0 && !merged) exit_[g] = st;
+        // A re-run that reaches the end of its segment without having merged holds the exact state there, so it
+        // simply keeps going into the next segment -- its exit IS that segment's true entry -- until it merges with the
+        // trajectory in place, as long as nobody else is re-running that segment in this round (redo flag clear: its
+        // own hand-off had been certified against the exit this chain has just replaced).  Without this every such
+        // miss costs one more host round that lasts as long as its slowest chain; slow-merging streams (carrier
+        // offset near zero) had 4-7 rounds.
+        int gg = g, jj = j;
+        while (!merged && redo && jj + 1 < nseg && !redo[gg + 1]) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                exit_[gg] = st;
+                entry[gg + 1] = st;
+            }
+            gg++;
+            jj++;
+            x += L;
+            y += L;
+            ck += ncp;
+            const int len2 = (int)min((long long)L, n - (long long)jj * L);
+            st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE>(x, y, 0, len2, st, prm, sh, ck, C, &merged, &iters);
+        }
+        if (threadIdx.x == 0 && !merged) exit_[gg] = st;
     }
     if (threadIdx.x == 0 && iters_total) atomicAdd(iters_total, iters);
 }

@@ -27,7 +27,8 @@ _NP_OF_TYPE = {XRD_FLOATIQ: np.float32, XRD_S16IQ: np.int16, XRD_S8IQ: np.int8, 
 ABI_SYMBOLS = [
     "xrd_config_defaults", "xrd_create", "xrd_destroy", "xrd_last_error", "xrd_add_samples", "xrd_process",
     "xrd_demod_batch", "xrd_demod_batch_i8", "xrd_demod_device", "xrd_soft_i8", "xrd_get_state", "xrd_set_state",
-    "xrd_checkpoint_size", "xrd_checkpoint_save", "xrd_checkpoint_load", "xrd_symbol_capacity", "xrd_reset", "xrd_stream",
+    "xrd_checkpoint_size", "xrd_checkpoint_save", "xrd_checkpoint_load", "xrd_symbol_capacity", "xrd_get_diag", "xrd_reset",
+    "xrd_stream",
     "xrd_set_tuning", "xrd_get_stats",
     "xrd_design_rrc", "xrd_design_lowpass", "xrd_mmse_table", "xrd_costas_gains",
     "xrd_fir_create", "xrd_agc_create", "xrd_costas_create", "xrd_clock_recovery_create", "xrd_stage_work",
@@ -60,13 +61,20 @@ class LoopState(C.Structure):
     ]
 
 
+class Diag(C.Structure):
+    _fields_ = [
+        ("n_frame", C.c_int32), ("frame", C.c_int8 * 1024), ("n_symbols", C.c_uint64), ("mean_abs_i", C.c_double),
+        ("mean_sq_i", C.c_double), ("mean_sq_q", C.c_double), ("snr_db", C.c_float), ("lock", C.c_float),
+    ]
+
+
 class Tuning(C.Structure):
     _fields_ = [
         ("agc_seg", C.c_int32), ("agc_warm", C.c_int32), ("costas_seg", C.c_int32), ("costas_warm", C.c_int32),
         ("mm_seg", C.c_int64), ("mm_warm", C.c_int64), ("mm_lanes", C.c_int32), ("mm_kernel", C.c_int32),
         ("mm_rerun", C.c_int32), ("mm_walk_lanes", C.c_int32), ("loop_kernel", C.c_int32), ("rerun_kernel", C.c_int32),
         ("h2d_pieces", C.c_int32), ("h2d_piece_min_ki", C.c_int32), ("costas_chains_per_sm", C.c_int32),
-        ("agc_chains_per_sm", C.c_int32),
+        ("agc_chains_per_sm", C.c_int32), ("agc_kernel", C.c_int32), ("chase", C.c_int32),
     ]
 
 
@@ -124,6 +132,7 @@ def lib():
     L.xrd_checkpoint_load.argtypes = [vp, vp, C.c_size_t]
     L.xrd_symbol_capacity.argtypes = [vp, C.c_size_t]
     L.xrd_symbol_capacity.restype = C.c_int64
+    L.xrd_get_diag.argtypes = [vp, C.c_int, C.POINTER(Diag)]
     L.xrd_reset.argtypes = [vp]
     L.xrd_stream.argtypes = [vp]
     L.xrd_stream.restype = vp
@@ -365,6 +374,12 @@ class Demodulator:
         st = LoopState()
         self._check(lib().xrd_get_state(self._h, channel, C.byref(st)))
         return st
+
+    def diag(self, channel=0):
+        """diagnostics of the last call (xrd_get_diag): DiagManager frame bytes, SNR / lock estimate"""
+        g = Diag()
+        self._check(lib().xrd_get_diag(self._h, channel, C.byref(g)))
+        return g
 
     def set_state(self, st, channel=0):
         """loop variables only (xrd_set_state); checkpoint()/restore() also carry the filter histories"""
