@@ -277,6 +277,41 @@ def test_chain_integer_sample_types(gpu, xrd, oracle, siggen, type_, conv):
     check_symbols(np.concatenate(got), ref, conv + " via add_samples")
 
 
+@pytest.mark.parametrize("conv", ["s16", "s8", "u8"])
+def test_decimated_chain_integer_ingest(gpu, xrd, oracle, siggen, conv):
+    """decimation 4: the decimator is the first kernel of the chain and reads the raw samples (S16 converts as the
+    polyphase kernel loads; S8 / U8 through the generic decimating kernel); two ragged calls, two channels"""
+    kw = dict(sample_rate=10000000, decimation=4)
+    xs = [make_signal("hrit10", 1 << 20, channel=c, amp=(0.3, 0.6))[1] for c in range(2)]
+    to = {"s16": siggen.to_s16, "s8": siggen.to_s8, "u8": siggen.to_u8}[conv]
+    back = {"s16": oracle.convert_s16, "s8": oracle.convert_s8, "u8": oracle.convert_u8}[conv]
+    type_ = {"s16": xrd.XRD_S16IQ, "s8": xrd.XRD_S8IQ, "u8": xrd.XRD_U8IQ}[conv]
+    raws = [to(x).reshape(-1, 2) for x in xs]
+    d = xrd.Demodulator(mode="hrit", n_channels=2, **kw)
+    cut = 400004
+    a = d.demod(np.stack([r[:cut] for r in raws]), type=type_)
+    b = d.demod(np.stack([r[cut:] for r in raws]), type=type_)
+    for c in range(2):
+        ref = oracle.Chain(oracle.config(True, **kw)).process(back(raws[c].reshape(-1)))
+        check_symbols(np.concatenate([a[c], b[c]]), ref, "decimated %s ingest, channel %d" % (conv, c))
+
+
+def test_s16_ingest_fused_and_fallback(gpu, xrd, oracle, siggen):
+    """S16 IQ with decimation 1: the AGC converts as it loads (default kernels), in copy/compute pieces as well; with a
+    non-default AGC kernel the samples take the separate conversion pass.  Same symbols every way."""
+    _, x = make_signal("hrit", 1 << 21, amp=(0.3, 0.6))
+    raw = siggen.to_s16(x)
+    ref = oracle.Chain(oracle.config(True)).process(oracle.convert_s16(raw))
+    for tune in (dict(), dict(h2d_pieces=3, h2d_piece_min_ki=100), dict(agc_kernel=4), dict(agc_kernel=1),
+                 dict(agc_seg=4096, agc_warm=512)):
+        d = xrd.Demodulator(mode="hrit")
+        if tune:
+            d.set_tuning(**tune)
+        cut = 2 * 1_000_001
+        got = np.concatenate([d.demod(raw[:cut], type=xrd.XRD_S16IQ), d.demod(raw[cut:], type=xrd.XRD_S16IQ)])
+        check_symbols(got, ref, "S16 ingest, tuning %r" % (tune,))
+
+
 def test_multi_channel_batch(gpu, xrd, oracle):
     """configs[4] in miniature: independent LRIT channels with distinct seeds in one call"""
     nch, n = 12, 1 << 18

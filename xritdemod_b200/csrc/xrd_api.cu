@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -272,39 +273,64 @@ struct FirStage {
             dim3 grid((unsigned)((n_out + FIR_TILE - 1) / FIR_TILE), nch);
             XRD_LAUNCH(c, fir1_kernel, grid, FIR_THREADS, smem, st, in, out, d_taps.as<float>(), ntaps, n_out, in_stride,
                        out_stride);
-        } else if (D >= 2 && D <= 5 && !force_generic) {
-#define XRD_FIR_POLY(DV)                                                                                               \
-    do {                                                                                                               \
-        const size_t smem = FirPoly<DV>::smem_bytes(ntaps);                                                            \
-        if (smem > 200 * 1024) break;                                                                                  \
-        XRD_CUDA(cudaFuncSetAttribute(fird_poly_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        dim3 grid((unsigned)((n_out + FirPoly<DV>::TILE - 1) / FirPoly<DV>::TILE), nch);                               \
-        XRD_LAUNCH(c, fird_poly_kernel<DV>, grid, FP_THREADS, smem, st, in, out, d_taps.as<float>(), ntaps, n_out,     \
-                   in_stride, out_stride);                                                                             \
-        return;                                                                                                        \
+        } else {
+            // decimating filters read their history from a separate buffer: run_decim
+            throw CudaError{"FirStage::run: decimating filters go through run_decim", XRD_E_ARG};
+        }
+    }
+    bool force_generic = false;
+
+    // Decimating filter (D > 1): `in` holds n_out * D samples of ingest format `type` per channel (x[0] first, channel
+    // stride in_stride samples), `hist` the ntaps - 1 cf32 samples before x[0] of every channel ([nch][ntaps - 1]); the
+    // history is advanced to the end of this call afterwards.  S16 input converts as it loads (polyphase kernels);
+    // S8 / U8 go through the generic kernel.
+    template <class IN>
+    void launch_decim(Counters &c, cudaStream_t st, const void *in_any, float2 *hist, float2 *out, long long n_out, int nch,
+                      long long in_stride, long long out_stride, bool poly_ok)
+    {
+        const typename IN::raw *in = static_cast<const typename IN::raw *>(in_any);
+        bool done = false;
+        if (poly_ok && D >= 2 && D <= 5 && !force_generic) {
+#define XRD_FIR_POLY(DV)                                                                                                    \
+    do {                                                                                                                    \
+        const size_t smem = FirPoly<DV>::smem_bytes(ntaps);                                                                 \
+        if (smem > 200 * 1024) break;                                                                                       \
+        XRD_CUDA(cudaFuncSetAttribute((fird_poly_kernel<DV, IN>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        dim3 grid((unsigned)((n_out + FirPoly<DV>::TILE - 1) / FirPoly<DV>::TILE), nch);                                    \
+        XRD_LAUNCH(c, (fird_poly_kernel<DV, IN>), grid, FP_THREADS, smem, st, in, hist, out, d_taps.as<float>(), ntaps,     \
+                   n_out, in_stride, out_stride);                                                                           \
+        done = true;                                                                                                        \
     } while (0)
             if (D == 2) XRD_FIR_POLY(2);
             else if (D == 3) XRD_FIR_POLY(3);
             else if (D == 4) XRD_FIR_POLY(4);
             else XRD_FIR_POLY(5);
 #undef XRD_FIR_POLY
-            run_generic(c, st, in, out, n_out, nch, in_stride, out_stride);
-        } else {
-            run_generic(c, st, in, out, n_out, nch, in_stride, out_stride);
         }
-    }
-    bool force_generic = false;
-    void run_generic(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n_out, int nch, long long in_stride,
-                     long long out_stride)
-    {
-        const int tp = (ntaps + 1) & ~1;
-        {
+        if (!done) {
+            const int tp = (ntaps + 1) & ~1;
             const size_t smem = sizeof(float) * tp + sizeof(float2) * ((size_t)(FIRD_TILE - 1) * D + 1 + ntaps - 1);
             if (smem > 48 * 1024)
-                XRD_CUDA(cudaFuncSetAttribute(fird_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                XRD_CUDA(cudaFuncSetAttribute(fird_kernel<IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dim3 grid((unsigned)((n_out + FIRD_TILE - 1) / FIRD_TILE), nch);
-            XRD_LAUNCH(c, fird_kernel, grid, FIR_THREADS, smem, st, in, out, d_taps.as<float>(), ntaps, D, n_out,
+            XRD_LAUNCH(c, fird_kernel<IN>, grid, FIR_THREADS, smem, st, in, hist, out, d_taps.as<float>(), ntaps, D, n_out,
                        in_stride, out_stride);
+        }
+        if (ntaps > 1)
+            XRD_LAUNCH(c, fir_hist_carry_kernel<IN>, nch, 256, sizeof(float2) * (ntaps - 1), st, in, hist, ntaps - 1, n_out * D,
+                       in_stride);
+    }
+    void run_decim(Counters &c, cudaStream_t st, const void *in, int type, float2 *hist, float2 *out, long long n_out, int nch,
+                   long long in_stride, long long out_stride)
+    {
+        if (n_out <= 0) return;
+        if (sizeof(float2) * (size_t)(ntaps - 1) > 200 * 1024) throw CudaError{"FirFilter: too many taps", XRD_E_ARG};
+        switch (type) {
+        case XRD_FLOATIQ: launch_decim<InF32>(c, st, in, hist, out, n_out, nch, in_stride, out_stride, true); break;
+        case XRD_S16IQ: launch_decim<InS16>(c, st, in, hist, out, n_out, nch, in_stride, out_stride, true); break;
+        case XRD_S8IQ: launch_decim<InS8>(c, st, in, hist, out, n_out, nch, in_stride, out_stride, false); break;
+        case XRD_U8IQ: launch_decim<InU8>(c, st, in, hist, out, n_out, nch, in_stride, out_stride, false); break;
+        default: throw CudaError{"FirFilter: unknown sample type", XRD_E_ARG};
         }
     }
 };
@@ -400,17 +426,41 @@ template <class LOOP> struct SegStage {
     void resolve_impl(Counters &, cudaStream_t, int, int, long long, AgcState *) {}
 
     long long hist = 0;   // samples of the same stream addressable before `in` (set by run)
-    void launch(Counters &c, cudaStream_t st, bool wn, const float2 *in, float2 *out, long long n, int Ls, int Ws, int nseg,
+    bool in_s16 = false;  // this call's `in` holds S16 IQ samples (AGC as the first kernel of the chain; set by run)
+    // the fused S16 ingest exists for the default kernel shapes of the AGC only
+    bool can_fuse_s16() const { return std::is_same<LOOP, AgcLoop>::value && use_wn && wn_variant == 2 && redo_variant == 4; }
+    void launch(Counters &c, cudaStream_t st, bool wn, const void *in_any, float2 *out, long long n, int Ls, int Ws, int nseg,
                 int n_work, int ncp, int mode, long long in_stride, long long out_stride)
     {
+        const float2 *in = static_cast<const float2 *>(in_any);
         const int variant = (mode == 1) ? redo_variant : wn_variant;
+        const unsigned char *redo_flags = (mode == 1 && chase) ? d_redo.as<unsigned char>() : (const unsigned char *)nullptr;
+        if constexpr (std::is_same<LOOP, AgcLoop>::value) {
+            if (in_s16) {
+                // converts as it loads: wn_loop_kernel / wn_cta_kernel on short2 samples (can_fuse_s16() was checked)
+                const short2 *in16 = static_cast<const short2 *>(in_any);
+                if (variant == 4) {
+                    XRD_LAUNCH(c, (wn_cta_kernel<LOOP, 2, 4, InS16>), n_work, 32 * 4, 0, st, in16, out, n, Ls, Ws, nseg, n_work,
+                               d_entry.template as<State>(), d_exit.template as<State>(), d_carried.template as<State>(),
+                               d_list.template as<int>(), d_ckpt.template as<State>(), ncp, WN_CKPT,
+                               d_iters.template as<unsigned long long>(), prm, mode, in_stride, out_stride, hist, redo_flags);
+                } else {
+                    const int grid = (n_work + WN_WARPS - 1) / WN_WARPS;
+                    XRD_LAUNCH(c, (wn_loop_kernel<LOOP, WN_K, InS16>), grid, WN_WARPS * 32, wn_smem_bytes<WN_K>(), st, in16, out, n,
+                               Ls, Ws, nseg, n_work, d_entry.template as<State>(), d_exit.template as<State>(),
+                               d_carried.template as<State>(), d_list.template as<int>(), d_ckpt.template as<State>(), ncp,
+                               WN_CKPT, d_iters.template as<unsigned long long>(), prm, mode, in_stride, out_stride, hist,
+                               (State *)nullptr, 0);
+                }
+                return;
+            }
+        }
         if (wn && variant >= 3) {
             // one CTA of WPC warps per chain (wn_cta_kernel<LOOP, K, WPC>)
 #define XRD_WN_CTA(KV, WV)                                                                                              \
     XRD_LAUNCH(c, (wn_cta_kernel<LOOP, KV, WV>), n_work, 32 * WV, 0, st, in, out, n, Ls, Ws, nseg, n_work,              \
                d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(), d_ckpt.as<State>(), ncp, \
-               WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride, hist,                        \
-               (mode == 1 && chase) ? d_redo.as<unsigned char>() : (const unsigned char *)nullptr)
+               WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride, hist, redo_flags)
             if (variant == 3) XRD_WN_CTA(1, 4);
             else if (variant == 4) XRD_WN_CTA(2, 4);
             else if (variant == 5) XRD_WN_CTA(1, 2);
@@ -433,10 +483,13 @@ template <class LOOP> struct SegStage {
 
     // hist_avail: samples of the same stream that are still in place right before `in` (an earlier piece of the
     // same call); speculative warm-ups of the window kernel may start there instead of at in[0]
-    void run(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n, long long in_stride,
-             long long out_stride, long long hist_avail = 0)
+    // s16: `in` holds S16 IQ samples instead of cf32 (caller checked can_fuse_s16())
+    void run(Counters &c, cudaStream_t st, const void *in_any, float2 *out, long long n, long long in_stride,
+             long long out_stride, long long hist_avail = 0, bool s16 = false)
     {
         if (n <= 0) return;
+        const float2 *in = static_cast<const float2 *>(in_any);
+        in_s16 = s16;
         const bool wn = use_wn;
         hist = wn ? hist_avail : 0;
         int Ls, Ws;
@@ -476,7 +529,7 @@ template <class LOOP> struct SegStage {
                     d_pre.ensure(sizeof(State) * nch);
                     d_adv0.ensure(sizeof(float) * nch);
                 }
-                launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 2, in_stride, out_stride);
+                launch(c, st, wn, in_any, out, n, Ls, Ws, nseg, (int)tot, ncp, 2, in_stride, out_stride);
                 const long long nblk = n / CPB;
                 d_psi.ensure(sizeof(float) * (size_t)nblk * nch);
                 d_adv.ensure(sizeof(float) * tot);
@@ -486,9 +539,9 @@ template <class LOOP> struct SegStage {
                 XRD_LAUNCH(c, costas_seg_advance_kernel, g2, 256, 0, st, d_psi.as<float>(), d_adv.as<float>(), nseg, Ls / CPB,
                            nblk, nblk, pre_len > 0 ? d_adv0.as<float>() : (float *)nullptr, pre_len / CPB);
                 resolve(c, st, nseg, Ls, (long long)Ws - hist);
-                launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 3, in_stride, out_stride);
+                launch(c, st, wn, in_any, out, n, Ls, Ws, nseg, (int)tot, ncp, 3, in_stride, out_stride);
             } else {
-                launch(c, st, wn, in, out, n, Ls, Ws, nseg, (int)tot, ncp, 0, in_stride, out_stride);
+                launch(c, st, wn, in_any, out, n, Ls, Ws, nseg, (int)tot, ncp, 0, in_stride, out_stride);
             }
             bool escalate = false;
             for (int round = 0; nseg > 1 && round < nseg; round++) {
@@ -509,7 +562,7 @@ template <class LOOP> struct SegStage {
                 }
                 rounds++;
                 redone += (uint64_t)nr;
-                launch(c, st, wn, in, out, n, Ls, Ws, nseg, nr, ncp, 1, in_stride, out_stride);
+                launch(c, st, wn, in_any, out, n, Ls, Ws, nseg, nr, ncp, 1, in_stride, out_stride);
             }
             if (!escalate) {
                 XRD_LAUNCH(c, (take_last_kernel<State>), (nch + 127) / 128, 128, 0, st, d_carried.as<State>(),
@@ -829,7 +882,8 @@ struct xrd_demod {
     SegStage<CostasLoopK> costas;
     MmStage mm;
     // chunk buffers; per-channel stride = prefix + capacity
-    DevBuf b_in, b_dec, b_agc, b_rrc, b_cos, b_sym, b_raw, b_i8;
+    DevBuf b_dec, b_agc, b_rrc, b_cos, b_sym, b_raw, b_i8;
+    DevBuf d_dec_hist;         // decimator history: the last ntaps_lpf - 1 input samples of every channel, cf32 (D > 1)
     long long cap_n = 0;       // input samples per channel the buffers are sized for
     bool hist_zeroed = false;
     std::vector<uint64_t> n_in, n_sym;
@@ -850,7 +904,6 @@ struct xrd_demod {
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
-    long long in_stride() const { return cap_n + dec.hist(); }
     long long agc_stride() const { return cap_n / D + rrc.hist(); }
     long long cos_stride() const { return cap_n / D + MM_TAIL; }
     long long nd_cap() const { return cap_n / D; }
@@ -858,20 +911,16 @@ struct xrd_demod {
     void ensure(long long n)
     {
         if (n <= cap_n) return;
-        // carried prefixes (FIR history, M&M tail) must survive a regrow
+        // carried prefixes (RRC history, M&M tail) must survive a regrow
         const long long old_cap = cap_n;
         const long long new_cap = n + n / 8;
-        std::vector<float2> keep_in, keep_agc, keep_cos;
-        const int Hd = (D > 1) ? dec.hist() : 0, Hr = rrc.hist();
+        std::vector<float2> keep_agc, keep_cos;
+        const int Hr = rrc.hist();
         if (old_cap > 0) {
             XRD_CUDA(cudaStreamSynchronize(stream));
-            keep_in.resize((size_t)nch * Hd);
             keep_agc.resize((size_t)nch * Hr);
             keep_cos.resize((size_t)nch * MM_TAIL);
             for (int ch = 0; ch < nch; ch++) {
-                if (Hd)
-                    XRD_CUDA(cudaMemcpy(keep_in.data() + (size_t)ch * Hd, b_in.as<float2>() + (size_t)ch * (old_cap + Hd),
-                                        sizeof(float2) * Hd, cudaMemcpyDeviceToHost));
                 XRD_CUDA(cudaMemcpy(keep_agc.data() + (size_t)ch * Hr,
                                     b_agc.as<float2>() + (size_t)ch * (old_cap / D + Hr), sizeof(float2) * Hr,
                                     cudaMemcpyDeviceToHost));
@@ -882,21 +931,11 @@ struct xrd_demod {
         }
         cap_n = new_cap - new_cap % D;
         const long long nd = cap_n / D;
-        if (D > 1) {
-            b_in.ensure(sizeof(float2) * (size_t)(cap_n + Hd) * nch);
-            b_dec.ensure(sizeof(float2) * (size_t)nd * nch);
-        }
+        if (D > 1) b_dec.ensure(sizeof(float2) * (size_t)nd * nch);
         b_agc.ensure(sizeof(float2) * (size_t)(nd + Hr) * nch);
         b_rrc.ensure(sizeof(float2) * (size_t)nd * nch);
         b_cos.ensure(sizeof(float2) * (size_t)(nd + MM_TAIL) * nch);
         for (int ch = 0; ch < nch; ch++) {
-            if (Hd) {
-                float2 *p = b_in.as<float2>() + (size_t)ch * (cap_n + Hd);
-                if (old_cap > 0)
-                    XRD_CUDA(cudaMemcpy(p, keep_in.data() + (size_t)ch * Hd, sizeof(float2) * Hd, cudaMemcpyHostToDevice));
-                else
-                    XRD_CUDA(cudaMemset(p, 0, sizeof(float2) * Hd));
-            }
             float2 *pa = b_agc.as<float2>() + (size_t)ch * (nd + Hr);
             float2 *pc = b_cos.as<float2>() + (size_t)ch * (nd + MM_TAIL);
             if (old_cap > 0) {
@@ -918,9 +957,9 @@ struct xrd_demod {
         costas.reset();
         mm.reset();
         const int Hd = (D > 1) ? dec.hist() : 0, Hr = rrc.hist();
+        if (Hd) XRD_CUDA(cudaMemset(d_dec_hist.p, 0, sizeof(float2) * (size_t)Hd * nch));
         if (cap_n > 0) {
             for (int ch = 0; ch < nch; ch++) {
-                if (Hd) XRD_CUDA(cudaMemset(b_in.as<float2>() + (size_t)ch * in_stride(), 0, sizeof(float2) * Hd));
                 XRD_CUDA(cudaMemset(b_agc.as<float2>() + (size_t)ch * agc_stride(), 0, sizeof(float2) * Hr));
                 XRD_CUDA(cudaMemset(b_cos.as<float2>() + (size_t)ch * cos_stride(), 0, sizeof(float2) * MM_TAIL));
             }
@@ -941,21 +980,35 @@ struct xrd_demod {
     void run_front(const void *iq_dev, long long n_total, long long off, long long m, int type)
     {
         const long long nd = m / D, nd_off = off / D;
-        const int Hd = (D > 1) ? dec.hist() : 0, Hr = rrc.hist();
-        const float2 *x = nullptr;   // AGC input, [nch] with stride xs
+        const int Hr = rrc.hist();
+        const void *x = nullptr;   // AGC input, [nch] with stride xs (samples)
         long long xs = 0;
-        if (D > 1 || type != XRD_FLOATIQ) {
-            // ingest into b_in (behind the decimator history); D == 1 reuses b_rrc as scratch
-            float2 *dst = (D > 1) ? b_in.as<float2>() + Hd : b_rrc.as<float2>();
-            const long long ds = (D > 1) ? in_stride() : nd_cap();
+        bool x_s16 = false;
+        if (D > 1) {
+            // the decimator is the first kernel of the chain: it reads the raw samples in their ingest format
+            t_dec.start(stream);
+            dec.run_decim(ctr, stream, iq_dev, type, d_dec_hist.as<float2>(), b_dec.as<float2>(), nd, nch, n_total, nd_cap());
+            t_dec.stop(stream);
+            x = b_dec.as<float2>();
+            xs = nd_cap();
+        } else if (type == XRD_FLOATIQ) {
+            x = (const float2 *)iq_dev + off;
+            xs = n_total;
+        } else if (type == XRD_S16IQ && agc.can_fuse_s16()) {
+            // the AGC is the first kernel: it converts as it loads
+            x = (const short2 *)iq_dev + off;
+            xs = n_total;
+            x_s16 = true;
+        } else {
+            // S8 / U8 (and S16 with non-default AGC kernels): one conversion pass into b_rrc, which the AGC has
+            // consumed by the time the RRC filter writes it
+            float2 *dst = b_rrc.as<float2>();
+            const long long ds = nd_cap();
             for (int ch = 0; ch < nch; ch++) {
                 float *o = reinterpret_cast<float *>(dst + (size_t)ch * ds);
                 const size_t nf = (size_t)m * 2;
                 const int blocks = (int)std::min<size_t>((nf + 1023) / 1024, 148 * 16);
-                if (type == XRD_FLOATIQ) {
-                    XRD_CUDA(cudaMemcpyAsync(o, (const float *)iq_dev + (size_t)ch * nf, sizeof(float) * nf,
-                                             cudaMemcpyDeviceToDevice, stream));
-                } else if (type == XRD_S16IQ) {
+                if (type == XRD_S16IQ) {
                     XRD_LAUNCH(ctr, (convert_kernel<short>), blocks, 256, 0, stream, (const short *)iq_dev + (size_t)ch * nf,
                                o, nf, 1.0f / 32768.f, 0.f);
                 } else if (type == XRD_S8IQ) {
@@ -968,22 +1021,10 @@ struct xrd_demod {
             }
             x = dst;
             xs = ds;
-        } else {
-            x = (const float2 *)iq_dev + off;
-            xs = n_total;
-        }
-        if (D > 1) {
-            t_dec.start(stream);
-            dec.run(ctr, stream, x, b_dec.as<float2>(), nd, nch, xs, nd_cap());
-            XRD_LAUNCH(ctr, carry_prefix_kernel, nch, 256, sizeof(float2) * Hd, stream, b_in.as<float2>(), Hd, m,
-                       in_stride());
-            t_dec.stop(stream);
-            x = b_dec.as<float2>();
-            xs = nd_cap();
         }
         float2 *agc_out = b_agc.as<float2>() + Hr + nd_off;
         t_agc.start(stream);
-        agc.run(ctr, stream, x, agc_out, nd, xs, agc_stride(), nd_off);
+        agc.run(ctr, stream, x, agc_out, nd, xs, agc_stride(), nd_off, x_s16);
         t_agc.stop(stream);
         t_rrc.start(stream);
         // (when D == 1 and the input was converted into b_rrc, AGC has consumed it by now)
@@ -1061,7 +1102,8 @@ struct xrd_demod {
         ensure(n);
         for (float &v : ms) v = 0.f;
         int pieces = 1;
-        if (type == XRD_FLOATIQ && D == 1 && nch == 1 && piece_min > 0) pieces = (int)std::min<long long>(max_pieces, n / piece_min);
+        if ((type == XRD_FLOATIQ || (type == XRD_S16IQ && agc.can_fuse_s16())) && D == 1 && nch == 1 && piece_min > 0)
+            pieces = (int)std::min<long long>(max_pieces, n / piece_min);
         if (pieces <= 1) {
             XRD_CUDA(cudaMemcpyAsync(b_raw.p, iq, sb * (size_t)n * nch, cudaMemcpyHostToDevice, stream));
             run_front(b_raw.p, n, 0, n, type);
@@ -1199,6 +1241,8 @@ int xrd_create(const xrd_config *cfg, xrd_demod **out)
         if (d->D > 1) {
             design_lowpass(1, (double)cfg->sample_rate, circuit / 2, 100e3, taps);            // :444
             d->dec.init(d->D, taps.data(), (int)taps.size());                                 // :446
+            d->d_dec_hist.ensure(sizeof(float2) * (size_t)d->dec.hist() * d->nch);
+            XRD_CUDA(cudaMemset(d->d_dec_hist.p, 0, sizeof(float2) * (size_t)d->dec.hist() * d->nch));
         }
         d->agc.prm = AgcParams{cfg->agc_rate, cfg->agc_ref, cfg->agc_max_gain};               // :447
         d->agc.L = 2048;
@@ -1553,7 +1597,10 @@ int xrd_checkpoint_save(xrd_demod *d, void *blob, size_t cap)
                 else memset(p, 0, sizeof(float2) * count);
                 p += sizeof(float2) * count;
             };
-            grab(d->b_in, d->in_stride(), Hd);
+            if (Hd) {   // the decimator history has its own buffer, valid from creation on
+                XRD_CUDA(cudaMemcpy(p, d->d_dec_hist.as<float2>() + (size_t)ch * Hd, sizeof(float2) * Hd, cudaMemcpyDeviceToHost));
+                p += sizeof(float2) * Hd;
+            }
             grab(d->b_agc, d->agc_stride(), Hr);
             grab(d->b_cos, d->cos_stride(), MM_TAIL);
         }
@@ -1597,7 +1644,7 @@ int xrd_checkpoint_load(xrd_demod *d, const void *blob, size_t bytes)
                 XRD_CUDA(cudaMemcpy(buf.as<float2>() + (size_t)ch * stride, p, sizeof(float2) * count, cudaMemcpyHostToDevice));
                 p += sizeof(float2) * count;
             };
-            put(d->b_in, d->in_stride(), Hd);
+            put(d->d_dec_hist, Hd, Hd);
             put(d->b_agc, d->agc_stride(), Hr);
             put(d->b_cos, d->cos_stride(), MM_TAIL);
         }
@@ -1868,7 +1915,10 @@ int xrd_stage_work(xrd_stage *s, const float *in, float *out, int length)
         long long n_copy = n_out;
         switch (s->kind) {
         case xrd_stage::FIR:
-            s->fir.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_out, 1, 0, 0, &s->b_in);
+            if (s->fir.D > 1)   // history = the prefix of b_in, right before x
+                s->fir.run_decim(s->ctr, s->stream, x, XRD_FLOATIQ, s->b_in.as<float2>(), s->b_out.as<float2>(), n_out, 1, 0, 0);
+            else
+                s->fir.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_out, 1, 0, 0, &s->b_in);
             break;
         case xrd_stage::AGC:
             s->agc.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_in, 0, 0);
@@ -1888,7 +1938,7 @@ int xrd_stage_work(xrd_stage *s, const float *in, float *out, int length)
             break;
         }
         }
-        if (s->prefix)
+        if (s->prefix && !(s->kind == xrd_stage::FIR && s->fir.D > 1))   // (run_decim has advanced its history itself)
             XRD_LAUNCH(s->ctr, carry_prefix_kernel, 1, 256, sizeof(float2) * s->prefix, s->stream, s->b_in.as<float2>(),
                        s->prefix, n_in, 0);
         XRD_CUDA(cudaMemcpyAsync(out, s->b_out.p, sizeof(float2) * n_copy, cudaMemcpyDeviceToHost, s->stream));

@@ -82,6 +82,29 @@ __global__ void convert_kernel(const T *__restrict__ in, float *__restrict__ out
         out[i] = ((float)in[i] - bias) * scale;   // small integers and a power-of-two scale: identical to the division
 }
 
+// The same conversions as loads: the first kernel of the chain (the decimator when decimation > 1, else the AGC)
+// reads the raw samples and converts them in registers, so integer input never takes a pass of its own.
+struct InF32 {
+    typedef float2 raw;
+    __device__ static __forceinline__ float2 cvt(float2 v) { return v; }
+};
+struct InS16 {
+    typedef short2 raw;
+    // v / 32768.f (demodulator.cpp:60-61); the scale is a power of two: identical to the division
+    __device__ static __forceinline__ float2 cvt(short2 v) { return make_float2((float)v.x * (1.0f / 32768.f), (float)v.y * (1.0f / 32768.f)); }
+};
+struct InS8 {
+    typedef char2 raw;
+    __device__ static __forceinline__ float2 cvt(char2 v) { return make_float2((float)v.x * (1.0f / 128.f), (float)v.y * (1.0f / 128.f)); }
+};
+struct InU8 {
+    typedef uchar2 raw;
+    __device__ static __forceinline__ float2 cvt(uchar2 v)
+    {
+        return make_float2(((float)v.x - 128.f) * (1.0f / 128.f), ((float)v.y - 128.f) * (1.0f / 128.f));
+    }
+};
+
 // ---------------------------------------------------------------------------------------
 // FIR (FirFilter::Work): out[i] = sum_k taps[k] * x[i*D - k], accumulated k = 0..T-1 by fmaf
 // from 0.  `in` points at x[0]; x[-1..-(T-1)] (history) must be addressable before it.
@@ -159,9 +182,13 @@ fir1_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float
 
 // generic decimation D >= 1: one output per thread-iteration straight from the staged tile
 constexpr int FIRD_TILE = 1024;  // outputs per CTA
+// `in` holds the samples of this call in their ingest format IN (x[0] first); the H = ntaps - 1 samples before x[0]
+// come from `hist` (cf32, hist[H + g] = x[g] for g < 0), which the host carries from call to call.
+template <class IN>
 __global__ void __launch_bounds__(FIR_THREADS)
-fird_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float *__restrict__ taps, int ntaps,
-            int D, long long n_out, long long in_ch_stride, long long out_ch_stride)
+fird_kernel(const typename IN::raw *__restrict__ in, const float2 *__restrict__ hist, float2 *__restrict__ out,
+            const float *__restrict__ taps, int ntaps, int D, long long n_out, long long in_ch_stride,
+            long long out_ch_stride)
 {
     extern __shared__ float s_mem[];
     const int H = ntaps - 1;
@@ -169,12 +196,16 @@ fird_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float
     float2 *s_x = reinterpret_cast<float2 *>(s_mem + ((ntaps + 1) & ~1));  // [(FIRD_TILE-1)*D + 1 + H]
     const int ch = blockIdx.y;
     in += (size_t)ch * in_ch_stride;
+    hist += (size_t)ch * H;
     out += (size_t)ch * out_ch_stride;
     const long long tile0 = (long long)blockIdx.x * FIRD_TILE;
     const int tile_n = (int)min((long long)FIRD_TILE, n_out - tile0);
     const int span = (tile_n - 1) * D + 1 + H;
     for (int i = threadIdx.x; i < ntaps; i += FIR_THREADS) s_taps[i] = taps[i];
-    for (int i = threadIdx.x; i < span; i += FIR_THREADS) s_x[i] = __ldg(in + tile0 * D - H + i);
+    for (int i = threadIdx.x; i < span; i += FIR_THREADS) {
+        const long long g = tile0 * D - H + i;
+        s_x[i] = (g >= 0) ? IN::cvt(__ldg(in + g)) : hist[H + g];
+    }
     __syncthreads();
     for (int o = threadIdx.x; o < tile_n; o += FIR_THREADS) {
         const float2 *x = s_x + o * D + H;
@@ -206,10 +237,11 @@ template <int D> struct FirPoly {
     }
 };
 
-template <int D>
+template <int D, class IN>
 __global__ void __launch_bounds__(FP_THREADS)
-fird_poly_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float *__restrict__ taps, int ntaps,
-                 long long n_out, long long in_ch_stride, long long out_ch_stride)
+fird_poly_kernel(const typename IN::raw *__restrict__ in, const float2 *__restrict__ hist, float2 *__restrict__ out,
+                 const float *__restrict__ taps, int ntaps, long long n_out, long long in_ch_stride,
+                 long long out_ch_stride)
 {
     constexpr int R = FirPoly<D>::R, TILE = FirPoly<D>::TILE;
     extern __shared__ float s_mem[];
@@ -219,6 +251,7 @@ fird_poly_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const 
     float2 *s_xp = reinterpret_cast<float2 *>(s_mem + ((M * D + 1) & ~1));
     const int ch = blockIdx.y;
     in += (size_t)ch * in_ch_stride;
+    hist += (size_t)ch * (ntaps - 1);
     out += (size_t)ch * out_ch_stride;
     const long long tile0 = (long long)blockIdx.x * TILE;
     const int tile_n = (int)min((long long)TILE, n_out - tile0);
@@ -234,7 +267,8 @@ fird_poly_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const 
         long long ip = (g >= 0) ? (g + D - 1) / D : -((-g) / D);
         const int p = (int)(ip * D - g);
         const int slot = (int)(ip - (tile0 - M));
-        s_xp[p * XL + slot] = (g >= g_min) ? __ldg(in + g) : make_float2(0.f, 0.f);
+        // samples before x[0] come from the carried history (hist[ntaps - 1 + g] = x[g])
+        s_xp[p * XL + slot] = (g >= g_min) ? ((g >= 0) ? IN::cvt(__ldg(in + g)) : hist[ntaps - 1 + g]) : make_float2(0.f, 0.f);
     }
     __syncthreads();
     const int o0 = threadIdx.x * R;
@@ -272,6 +306,22 @@ fird_poly_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const 
 #pragma unroll
     for (int r = 0; r < R; r++)
         if (o0 + r < tile_n) out[tile0 + o0 + r] = acc[r];
+}
+
+// next call's decimator history: the last H samples of [hist | x[0..n)], converted (H <= 1024 per CTA pass)
+template <class IN>
+__global__ void fir_hist_carry_kernel(const typename IN::raw *__restrict__ in, float2 *__restrict__ hist, int H, long long n,
+                                      long long in_ch_stride)
+{
+    extern __shared__ float2 s_keep[];
+    in += (size_t)blockIdx.x * in_ch_stride;
+    hist += (size_t)blockIdx.x * H;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        const long long g = n - H + i;   // index into x of the sample that becomes hist[i]
+        s_keep[i] = (g >= 0) ? IN::cvt(__ldg(in + g)) : hist[H + g];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) hist[i] = s_keep[i];
 }
 
 // ---------------------------------------------------------------------------------------

@@ -68,7 +68,7 @@ struct CostasWn {
         p = (p < -T) ? p + T : p;
         // a NaN phase (non-finite input) stays NaN: that IS the literal loop's state from then on
         f[0] = (p != p) ? p : ((p > T || p < -T) ? 0.0 : p);
-        f[1] = fmin(fmax(f[1], -1.0), 1.0);
+        f[1] = (f[1] != f[1]) ? f[1] : fmin(fmax(f[1], -1.0), 1.0);
     }
     __device__ static __forceinline__ void extrapolate(const double *e, int r, double *o)
     {
@@ -109,10 +109,21 @@ template <class State> __device__ __forceinline__ State wn_shfl(const State &v, 
 // Slot lane*K + k of the ring holds one sample; the base (oldest unfinished sample) always sits in
 // slot 0 of a lane (the window slides by multiples of K; up to K-1 accepted samples stay in the
 // window one more round), so a slot's rank is ((lane - tbl) & 31) * K + k.
-template <class LOOP, int K, bool WRITE, int CK>
-__device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, int s_end,
-                                                       typename LOOP::State st, const typename LOOP::Params &prm, float2 *ring,
-                                                       typename LOOP::State *ck, int C, bool *merged, unsigned long long *iters_out)
+// cp.async of one raw sample (8 bytes cf32, 4 bytes s16 IQ)
+template <class RAW> __device__ __forceinline__ void cp_async_raw(RAW *smem_dst, const RAW *gmem_src)
+{
+    static_assert(sizeof(RAW) == 8 || sizeof(RAW) == 4, "ring samples are staged with 8- or 4-byte cp.async");
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(RAW) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+// IN: ingest format of x (InF32, or InS16 when the AGC is the first kernel of the chain and converts as it loads)
+template <class LOOP, int K, bool WRITE, int CK, class IN = InF32>
+__device__ __forceinline__ typename LOOP::State wn_run(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s_begin,
+                                                       int s_end, typename LOOP::State st, const typename LOOP::Params &prm,
+                                                       typename IN::raw *ring, typename LOOP::State *ck, int C, bool *merged,
+                                                       unsigned long long *iters_out)
 {
     typedef typename LOOP::State State;
     typedef typename WnOf<LOOP>::type WN;
@@ -133,7 +144,7 @@ __device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict_
     int fill = s_begin;
     {
         const int target = min(s_begin + NT + MARGIN, s_end);
-        for (int i = fill + lane; i < target; i += 32) cp_async8(&ring[i & (RS - 1)], x + i);
+        for (int i = fill + lane; i < target; i += 32) cp_async_raw(&ring[i & (RS - 1)], x + i);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         fill = max(fill, target);
         cp_async_wait_all();
@@ -147,7 +158,7 @@ __device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict_
         WN::normalise(f);
         bs[k] = (r == 0) ? st : WN::narrow(f);
         const int i = base + r;
-        xs[k] = (i < s_end) ? ring[i & (RS - 1)] : make_float2(0.f, 0.f);
+        xs[k] = (i < s_end) ? IN::cvt(ring[i & (RS - 1)]) : make_float2(0.f, 0.f);
     }
     unsigned long long iters = 0;
     bool done_merged = false;
@@ -270,7 +281,7 @@ __device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict_
             // the freed slots' samples: base + NT + lr .. +K-1 (contiguous in the ring: lr, base and RS are multiples of K)
             const int i0 = base + NT + lr;
 #pragma unroll
-            for (int k = 0; k < K; k++) xs[k] = (i0 + k < s_end) ? ring[(i0 & (RS - 1)) + k] : make_float2(0.f, 0.f);
+            for (int k = 0; k < K; k++) xs[k] = (i0 + k < s_end) ? IN::cvt(ring[(i0 & (RS - 1)) + k]) : make_float2(0.f, 0.f);
         }
         bool odd = false;
         State nbs[K];
@@ -281,15 +292,6 @@ __device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict_
             for (int c = 0; c < NS; c++) f[c] = k ? pb[c] + li[k - 1][c] : pb[c];
             nbs[k] = WN::narrow(f);
             odd |= !WN::in_range(nbs[k]);
-        }
-        if (!freed && lr <= A) {
-            // the one lane that holds the end of the accepted run: verified slots keep their state, the
-            // first unaccepted slot takes the literal o[A-1]
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                if (lr + k < A) nbs[k] = bs[k];
-                else if (lr + k == A) nbs[k] = prev[k];
-            }
         }
         if (odd) {
             // rare: a believed phase of this lane left the loop's range; bring those back by whole turns
@@ -304,6 +306,16 @@ __device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict_
                 }
             }
         }
+        if (!freed && lr <= A) {
+            // the one lane that holds the end of the accepted run: verified slots keep their state, the
+            // first unaccepted slot takes the literal o[A-1].  Applied LAST: whatever the literal value is (a NaN
+            // after a non-finite sample is "out of range" too) it must survive, or the run would never advance.
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (lr + k < A) nbs[k] = bs[k];
+                else if (lr + k == A) nbs[k] = prev[k];
+            }
+        }
 #pragma unroll
         for (int k = 0; k < K; k++) bs[k] = nbs[k];
         if (Ap) {
@@ -311,7 +323,7 @@ __device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict_
             tbl = (tbl + Ap / K) & 31;
             base += Ap;
             const int target = min(base + NT + MARGIN, s_end);
-            for (int i = fill + lane; i < target; i += 32) cp_async8(&ring[i & (RS - 1)], x + i);
+            for (int i = fill + lane; i < target; i += 32) cp_async_raw(&ring[i & (RS - 1)], x + i);
             asm volatile("cp.async.commit_group;\n" ::: "memory");
             fill = max(fill, target);
         }
@@ -329,9 +341,9 @@ __device__ __forceinline__ typename LOOP::State wn_run(const float2 *__restrict_
 // it has merged with the trajectory already in place, and the first pass in two halves -- mode 2:
 // warm-ups only (entry states), mode 3: every segment from entry[g] -- so that the host can put
 // the Costas entries on one carrier-phase branch in between (costas_resolve_kernel).
-template <class LOOP, int K>
+template <class LOOP, int K, class IN = InF32>
 __global__ void __launch_bounds__(WN_WARPS * 32)
-wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, int L, int W, int nseg, int n_work,
+wn_loop_kernel(const typename IN::raw *__restrict__ in, float2 *__restrict__ out, long long n, int L, int W, int nseg, int n_work,
                typename LOOP::State *__restrict__ entry, typename LOOP::State *__restrict__ exit_,
                const typename LOOP::State *__restrict__ carried, const int *__restrict__ list,
                typename LOOP::State *__restrict__ ckpt, int ncp, int C, unsigned long long *__restrict__ iters_total,
@@ -341,14 +353,14 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
     extern __shared__ __align__(16) unsigned char wn_smem[];
     typedef typename LOOP::State State;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2 *ring = reinterpret_cast<float2 *>(wn_smem) + (size_t)wid * wn_ring<K>();
+    typename IN::raw *ring = reinterpret_cast<typename IN::raw *>(wn_smem) + (size_t)wid * wn_ring<K>();
     const int w = blockIdx.x * WN_WARPS + wid;
     if (w >= n_work) return;
     const int g = (mode == 1) ? list[w] : w;
     const int ch = g / nseg, j = g - ch * nseg;
     const long long seg0 = (long long)j * L;
     const int len = (int)min((long long)L, n - seg0);
-    const float2 *x = in + (size_t)ch * in_ch_stride + seg0;
+    const typename IN::raw *x = in + (size_t)ch * in_ch_stride + seg0;
     float2 *y = out + (size_t)ch * out_ch_stride + seg0;
     State *ck = ckpt + (size_t)g * ncp;
     unsigned long long iters = 0;
@@ -365,27 +377,27 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
             s_begin = -W;
             float2 first[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) first[i] = __ldg(x + s_begin + i);
+            for (int i = 0; i < 16; i++) first[i] = IN::cvt(__ldg(x + s_begin + i));
             st = LOOP::guess(prm, first, 16);
         }
-        if (s_begin < 0) st = wn_run<LOOP, K, false, WN_CK_NONE>(x, y, s_begin, 0, st, prm, ring, nullptr, C, nullptr, &iters);
+        if (s_begin < 0) st = wn_run<LOOP, K, false, WN_CK_NONE, IN>(x, y, s_begin, 0, st, prm, ring, nullptr, C, nullptr, &iters);
         if (lane == 0) entry[g] = st;
         // mode 2, first segment of a channel: it has no warm-up (its entry is the carried state, which right after a
         // reset is not locked yet), so run its first pre_len samples here, next to the others' warm-ups, and leave the
         // state reached -- the TRUE trajectory's, acquisition included -- for the branch resolution to refer to
         if (mode == 2 && pre && j == 0 && pre_len > 0 && pre_len <= len) {
-            const State p = wn_run<LOOP, K, false, WN_CK_NONE>(x, y, 0, pre_len, st, prm, ring, nullptr, C, nullptr, &iters);
+            const State p = wn_run<LOOP, K, false, WN_CK_NONE, IN>(x, y, 0, pre_len, st, prm, ring, nullptr, C, nullptr, &iters);
             if (lane == 0) pre[ch] = p;
         }
     }
     if (mode == 3) st = entry[g];
     if (mode == 0 || mode == 3) {
-        st = wn_run<LOOP, K, true, WN_CK_RECORD>(x, y, 0, len, st, prm, ring, ck, C, nullptr, &iters);
+        st = wn_run<LOOP, K, true, WN_CK_RECORD, IN>(x, y, 0, len, st, prm, ring, ck, C, nullptr, &iters);
         if (lane == 0) exit_[g] = st;
     } else if (mode == 1) {
         st = entry[g];
         bool merged = false;
-        st = wn_run<LOOP, K, true, WN_CK_COMPARE>(x, y, 0, len, st, prm, ring, ck, C, &merged, &iters);
+        st = wn_run<LOOP, K, true, WN_CK_COMPARE, IN>(x, y, 0, len, st, prm, ring, ck, C, &merged, &iters);
         if (lane == 0 && !merged) exit_[g] = st;
     }
     if (lane == 0 && iters_total) atomicAdd(iters_total, iters);
@@ -401,14 +413,14 @@ wn_loop_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
 // number of segments.  Two CTA barriers per iteration; everything exchanged between threads goes
 // through double-buffered shared memory and every thread derives the (uniform) control state itself.
 // ---------------------------------------------------------------------------------------
-template <class LOOP, int K, int WPC> struct WnCta {
+template <class LOOP, int K, int WPC, class IN = InF32> struct WnCta {
     typedef typename LOOP::State State;
     static constexpr int T = 32 * WPC;        // threads
     static constexpr int NT = T * K;          // slots
     static constexpr int RS = 4 * NT;         // ring samples
     static constexpr int NS = WnOf<LOOP>::type::NS;
     struct Shared {
-        float2 ring[RS];
+        typename IN::raw ring[RS];
         State o[2][NT];            // literal step results of every slot
         double tot[2][WPC][NS];    // warp totals of the differences
         double bex[2][NS];         // in-warp exclusive prefix of the base thread
@@ -416,15 +428,15 @@ template <class LOOP, int K, int WPC> struct WnCta {
     };
 };
 
-template <class LOOP, int K, int WPC, bool WRITE, int CK>
+template <class LOOP, int K, int WPC, bool WRITE, int CK, class IN = InF32>
 __device__ __forceinline__ typename LOOP::State
-wn_run_cta(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, int s_end, typename LOOP::State st,
-           const typename LOOP::Params &prm, typename WnCta<LOOP, K, WPC>::Shared &sh, typename LOOP::State *ck, int C,
+wn_run_cta(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s_begin, int s_end, typename LOOP::State st,
+           const typename LOOP::Params &prm, typename WnCta<LOOP, K, WPC, IN>::Shared &sh, typename LOOP::State *ck, int C,
            bool *merged, unsigned long long *iters_out)
 {
     typedef typename LOOP::State State;
     typedef typename WnOf<LOOP>::type WN;
-    typedef WnCta<LOOP, K, WPC> G;
+    typedef WnCta<LOOP, K, WPC, IN> G;
     constexpr int NS = G::NS, T = G::T, NT = G::NT, RS = G::RS, MARGIN = 2 * NT;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
 
@@ -440,7 +452,7 @@ wn_run_cta(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, in
     int fill = s_begin;
     {
         const int target = min(s_begin + NT + MARGIN, s_end);
-        for (int i = fill + t; i < target; i += T) cp_async8(&sh.ring[i & (RS - 1)], x + i);
+        for (int i = fill + t; i < target; i += T) cp_async_raw(&sh.ring[i & (RS - 1)], x + i);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         fill = max(fill, target);
         cp_async_wait_all();
@@ -454,7 +466,7 @@ wn_run_cta(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, in
         WN::normalise(f);
         bs[k] = (r == 0) ? st : WN::narrow(f);
         const int i = base + r;
-        xs[k] = (i < s_end) ? sh.ring[i & (RS - 1)] : make_float2(0.f, 0.f);
+        xs[k] = (i < s_end) ? IN::cvt(sh.ring[i & (RS - 1)]) : make_float2(0.f, 0.f);
     }
     unsigned long long iters = 0;
     bool done_merged = false;
@@ -587,7 +599,7 @@ wn_run_cta(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, in
             }
             const int i0 = base + NT + lr;
 #pragma unroll
-            for (int k = 0; k < K; k++) xs[k] = (i0 + k < s_end) ? sh.ring[(i0 & (RS - 1)) + k] : make_float2(0.f, 0.f);
+            for (int k = 0; k < K; k++) xs[k] = (i0 + k < s_end) ? IN::cvt(sh.ring[(i0 & (RS - 1)) + k]) : make_float2(0.f, 0.f);
         }
         bool odd = false;
         State nbs[K];
@@ -598,13 +610,6 @@ wn_run_cta(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, in
             for (int c = 0; c < NS; c++) f[c] = k ? pb[c] + li[k - 1][c] : pb[c];
             nbs[k] = WN::narrow(f);
             odd |= !WN::in_range(nbs[k]);
-        }
-        if (!freed && lr <= A) {
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                if (lr + k < A) nbs[k] = bs[k];
-                else if (lr + k == A) nbs[k] = prev[k];
-            }
         }
         if (odd) {
 #pragma unroll
@@ -618,6 +623,13 @@ wn_run_cta(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, in
                 }
             }
         }
+        if (!freed && lr <= A) {   // last, so that the literal value survives whatever it is (see wn_run)
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (lr + k < A) nbs[k] = bs[k];
+                else if (lr + k == A) nbs[k] = prev[k];
+            }
+        }
 #pragma unroll
         for (int k = 0; k < K; k++) bs[k] = nbs[k];
         if (Ap) {
@@ -625,7 +637,7 @@ wn_run_cta(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, in
             tbt = (tbt + Ap / K) & (T - 1);
             base += Ap;
             const int target = min(base + NT + MARGIN, s_end);
-            for (int i = fill + t; i < target; i += T) cp_async8(&sh.ring[i & (RS - 1)], x + i);
+            for (int i = fill + t; i < target; i += T) cp_async_raw(&sh.ring[i & (RS - 1)], x + i);
             asm volatile("cp.async.commit_group;\n" ::: "memory");
             fill = max(fill, target);
         }
@@ -640,9 +652,9 @@ wn_run_cta(const float2 *__restrict__ x, float2 *__restrict__ y, int s_begin, in
 }
 
 // one CTA per work item; contract and modes of wn_loop_kernel
-template <class LOOP, int K, int WPC>
+template <class LOOP, int K, int WPC, class IN = InF32>
 __global__ void __launch_bounds__(32 * WPC)
-wn_cta_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, int L, int W, int nseg, int n_work,
+wn_cta_kernel(const typename IN::raw *__restrict__ in, float2 *__restrict__ out, long long n, int L, int W, int nseg, int n_work,
               typename LOOP::State *__restrict__ entry, typename LOOP::State *__restrict__ exit_,
               const typename LOOP::State *__restrict__ carried, const int *__restrict__ list,
               typename LOOP::State *__restrict__ ckpt, int ncp, int C, unsigned long long *__restrict__ iters_total,
@@ -650,14 +662,14 @@ wn_cta_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long
               const unsigned char *__restrict__ redo)
 {
     typedef typename LOOP::State State;
-    __shared__ __align__(16) typename WnCta<LOOP, K, WPC>::Shared sh;
+    __shared__ __align__(16) typename WnCta<LOOP, K, WPC, IN>::Shared sh;
     const int w = blockIdx.x;
     if (w >= n_work) return;
     const int g = (mode == 1) ? list[w] : w;
     const int ch = g / nseg, j = g - ch * nseg;
     const long long seg0 = (long long)j * L;
     const int len = (int)min((long long)L, n - seg0);
-    const float2 *x = in + (size_t)ch * in_ch_stride + seg0;
+    const typename IN::raw *x = in + (size_t)ch * in_ch_stride + seg0;
     float2 *y = out + (size_t)ch * out_ch_stride + seg0;
     State *ck = ckpt + (size_t)g * ncp;
     unsigned long long iters = 0;
@@ -672,21 +684,21 @@ wn_cta_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long
             s_begin = -W;
             float2 first[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) first[i] = __ldg(x + s_begin + i);
+            for (int i = 0; i < 16; i++) first[i] = IN::cvt(__ldg(x + s_begin + i));
             st = LOOP::guess(prm, first, 16);
         }
         if (s_begin < 0)
-            st = wn_run_cta<LOOP, K, WPC, false, WN_CK_NONE>(x, y, s_begin, 0, st, prm, sh, nullptr, C, nullptr, &iters);
+            st = wn_run_cta<LOOP, K, WPC, false, WN_CK_NONE, IN>(x, y, s_begin, 0, st, prm, sh, nullptr, C, nullptr, &iters);
         if (threadIdx.x == 0) entry[g] = st;
     }
     if (mode == 3) st = entry[g];
     if (mode == 0 || mode == 3) {
-        st = wn_run_cta<LOOP, K, WPC, true, WN_CK_RECORD>(x, y, 0, len, st, prm, sh, ck, C, nullptr, &iters);
+        st = wn_run_cta<LOOP, K, WPC, true, WN_CK_RECORD, IN>(x, y, 0, len, st, prm, sh, ck, C, nullptr, &iters);
         if (threadIdx.x == 0) exit_[g] = st;
     } else if (mode == 1) {
         st = entry[g];
         bool merged = false;
-        st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE>(x, y, 0, len, st, prm, sh, ck, C, &merged, &iters);
+        st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE, IN>(x, y, 0, len, st, prm, sh, ck, C, &merged, &iters);
         // A re-run that reaches the end of its segment without having merged holds the exact state there, so it
         // simply keeps going into the next segment -- its exit IS that segment's true entry -- until it merges with the
         // trajectory in place, as long as nobody else is re-running that segment in this round (redo flag clear: its
@@ -706,7 +718,7 @@ wn_cta_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long
             y += L;
             ck += ncp;
             const int len2 = (int)min((long long)L, n - (long long)jj * L);
-            st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE>(x, y, 0, len2, st, prm, sh, ck, C, &merged, &iters);
+            st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE, IN>(x, y, 0, len2, st, prm, sh, ck, C, &merged, &iters);
         }
         if (threadIdx.x == 0 && !merged) exit_[gg] = st;
     }
