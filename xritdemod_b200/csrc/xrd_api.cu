@@ -221,18 +221,21 @@ struct FirStage {
         ntaps = n;
         d_taps.ensure(sizeof(float) * n);
         XRD_CUDA(cudaMemcpy(d_taps.p, taps, sizeof(float) * n, cudaMemcpyHostToDevice));
+        memset(&tma_taps, 0, sizeof tma_taps);
+        for (int k = 0; k < n && k < FT_MAX_TAPS; k++) tma_taps.h2[k] = make_float2(taps[k], taps[k]);
     }
     int hist() const { return ntaps - 1; }
     // TMA path of the stride-1 filter: tensor map of the allocation the input lives in, re-encoded when it moves
     bool use_tma = true;
     CUtensorMap tmap;
+    FtTaps tma_taps;
     const void *tmap_base = nullptr;
     size_t tmap_bytes = 0;
     int tma_ctas_per_sm = 0, sm_count = 0;
     bool run_tma(Counters &c, cudaStream_t st, const float2 *in, float2 *out, long long n_out, int nch, long long in_stride,
                  long long out_stride, const DevBuf *src)
     {
-        if (!use_tma || !src || !src->p || ft_rows(ntaps) > 256) return false;
+        if (!use_tma || !src || !src->p || ft_rows(ntaps) > 256 || ntaps > FT_MAX_TAPS) return false;
         const size_t smem = ft_smem_bytes(ntaps);
         if (smem > 200 * 1024) return false;
         const float2 *base = src->as<float2>();
@@ -254,7 +257,7 @@ struct FirStage {
         const long long n_tiles = tiles_per_ch * nch;
         if (n_tiles > 0x7fffffffLL) return false;
         const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * tma_ctas_per_sm);
-        XRD_LAUNCH(c, fir_tma_kernel, grid, FT_THREADS, smem, st, tmap, out, d_taps.as<float>(), ntaps, n_out,
+        XRD_LAUNCH(c, fir_tma_kernel, grid, FT_THREADS, smem, st, tmap, tma_taps, out, ntaps, n_out,
                    (long long)(in - base), in_stride, out_stride, (int)tiles_per_ch, (int)n_tiles);
         return true;
     }

@@ -6,16 +6,17 @@
 // The sample buffer is described to the TMA as a 2-D tensor of floats, 256 floats (128 cf32
 // samples, 1 KB) per row; a tile of FT_TILE outputs needs the FT_TILE + ntaps - 1 samples that
 // end at its last output, i.e. at most ft_rows(ntaps) whole rows starting at the row that holds
-// its first history sample.  One elected thread per CTA arms the stage's mbarrier with the byte
-// count and issues ONE bulk tensor copy per tile; the 256 threads then run the same register
-// sliding window as fir1_kernel out of shared memory (thread t owns 9 consecutive outputs; I and
-// Q accumulate in one packed FFMA2, taps k = 0..T-1 by fmaf from zero -- the oracle's order, so
-// the result is bit-identical).  Rows past the end of the allocation are zero-filled by the TMA
-// and only ever feed outputs that are not stored.
+// its first history sample.  A producer warp arms the stage's `full` mbarrier with the byte count
+// and issues ONE bulk tensor copy per tile, up to three tiles ahead; eight consumer warps run the
+// same register sliding window as fir1_kernel out of shared memory (thread t owns 9 consecutive
+// outputs; I and Q accumulate in one packed FFMA2, taps k = 0..T-1 by fmaf from zero -- the
+// oracle's order, so the result is bit-identical) and hand the stage back through its `empty`
+// mbarrier warp by warp: there is no CTA-wide barrier in the loop.  Taps are a kernel parameter
+// (constant bank), already duplicated into the (h, h) pairs FFMA2 wants.  Rows past the end of the
+// allocation are zero-filled by the TMA and only ever feed outputs that are not stored.
 //
 // Persistent: grid = CTAs resident on the device; CTA b takes tiles b, b + grid, b + 2 grid, ...
-// (of all channels), taps are loaded once per CTA, and the copy of tile i + 2 is in flight while
-// tiles i and i + 1 are computed.
+// (of all channels).
 #pragma once
 #include <cuda.h>
 
@@ -23,12 +24,24 @@
 
 namespace xrd {
 
-constexpr int FT_THREADS = 256;
+constexpr int FT_WARPS = 8;                  // consumer warps per CTA
+constexpr int FT_CONSUMERS = FT_WARPS * 32;
+constexpr int FT_THREADS = FT_CONSUMERS + 32; // + one producer warp (one lane issues the copies)
 constexpr int FT_R = 9;                      // outputs per thread (odd: conflict-free 8-byte shared loads)
-constexpr int FT_TILE = FT_THREADS * FT_R;   // outputs per tile
+constexpr int FT_TILE = FT_CONSUMERS * FT_R; // outputs per tile
 constexpr int FT_ROW = 128;                  // samples per tensor row (1 KB)
-constexpr int FT_STAGES = 2;
-constexpr int FT_HEAD = 128;                 // bytes before the first stage: two mbarriers, and slot -1 of stage 0
+#ifndef XRD_FT_STAGES
+#define XRD_FT_STAGES 2
+#endif
+constexpr int FT_STAGES = XRD_FT_STAGES;
+constexpr int FT_HEAD = 128;                 // bytes before the first stage: the mbarriers, and slot -1 of stage 0
+constexpr int FT_MAX_TAPS = 256;
+
+// taps travel as a kernel parameter (constant bank): every FFMA2 needs its tap as an (h, h) pair, and a uniform
+// constant load delivers exactly that without a shared-memory wavefront or a register move
+struct FtTaps {
+    float2 h2[FT_MAX_TAPS];
+};
 
 __host__ __device__ inline int ft_rows(int ntaps)
 {
@@ -37,7 +50,7 @@ __host__ __device__ inline int ft_rows(int ntaps)
 }
 __host__ __device__ inline size_t ft_smem_bytes(int ntaps)
 {
-    return FT_HEAD + (size_t)FT_STAGES * ft_rows(ntaps) * FT_ROW * sizeof(float2) + sizeof(float) * (size_t)((ntaps + 3) & ~3);
+    return FT_HEAD + (size_t)FT_STAGES * ft_rows(ntaps) * FT_ROW * sizeof(float2);
 }
 
 __device__ __forceinline__ void ft_mbar_init(uint64_t *bar, unsigned count)
@@ -48,6 +61,10 @@ __device__ __forceinline__ void ft_mbar_expect_tx(uint64_t *bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void ft_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void ft_mbar_wait(uint64_t *bar, unsigned parity)
 {
@@ -78,23 +95,27 @@ __device__ __forceinline__ void ft_tma_load_rows(void *smem_dst, const CUtensorM
         : "memory");
 }
 
+// Warp-specialised: the producer warp runs FT_STAGES tiles ahead (it waits for a stage's `empty` barrier, which the
+// eight consumer warps arrive on one by one as they finish with it, then arms `full` and issues the copy); a consumer
+// warp waits for `full`, computes its 288 outputs of the tile and moves on -- no CTA-wide barrier in the loop.
 __global__ void __launch_bounds__(FT_THREADS)
-fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, float2 *__restrict__ out, const float *__restrict__ taps, int ntaps,
+fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FtTaps taps, float2 *__restrict__ out, int ntaps,
                long long n_out, long long in_off /* samples from the tensor base to x[0] of channel 0 */,
                long long in_ch_stride, long long out_ch_stride, int tiles_per_ch, int n_tiles)
 {
     extern __shared__ __align__(128) unsigned char ft_smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(ft_smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ft_smem);          // [FT_STAGES]
+    uint64_t *empty = full + FT_STAGES;                              // [FT_STAGES]
     const int H = ntaps - 1;
     const int rows = ft_rows(ntaps);
     const int stage_elems = rows * FT_ROW;
     float2 *buf0 = reinterpret_cast<float2 *>(ft_smem + FT_HEAD);
-    float *s_taps = reinterpret_cast<float *>(ft_smem + FT_HEAD + (size_t)FT_STAGES * stage_elems * sizeof(float2));
     const int tid = threadIdx.x;
-    for (int i = tid; i < ntaps; i += FT_THREADS) s_taps[i] = taps[i];
     if (tid == 0) {
-        ft_mbar_init(&bar[0], 1);
-        ft_mbar_init(&bar[1], 1);
+        for (int s = 0; s < FT_STAGES; s++) {
+            ft_mbar_init(&full[s], 1);
+            ft_mbar_init(&empty[s], FT_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -105,30 +126,37 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, float2 *__restrict__ ou
         tile0 = (long long)(tile - ch * tiles_per_ch) * FT_TILE;
         return in_off + (long long)ch * in_ch_stride + tile0 - H;
     };
-    auto issue = [&](int tile, int s) {
-        int ch;
-        long long tile0;
-        const long long g0 = tile_origin(tile, ch, tile0);
-        ft_mbar_expect_tx(&bar[s], (unsigned)(stage_elems * sizeof(float2)));
-        ft_tma_load_rows(buf0 + (size_t)s * stage_elems, &tmap, (int)(g0 / FT_ROW), &bar[s]);
-    };
-    if (tid == 0) {
-        for (int s = 0; s < FT_STAGES; s++) {
-            const int tile = blockIdx.x + s * gridDim.x;
-            if (tile < n_tiles) issue(tile, s);
+
+    if (tid >= FT_CONSUMERS) {
+        // ---- producer warp
+        if (tid == FT_CONSUMERS) {
+            for (int it = 0;; it++) {
+                const int tile = blockIdx.x + it * gridDim.x;
+                if (tile >= n_tiles) break;
+                const int s = it % FT_STAGES, use = it / FT_STAGES;
+                if (use > 0) ft_mbar_wait(&empty[s], (unsigned)((use - 1) & 1));   // every consumer warp is done with it
+                int ch;
+                long long tile0;
+                const long long g0 = tile_origin(tile, ch, tile0);
+                ft_mbar_expect_tx(&full[s], (unsigned)(stage_elems * sizeof(float2)));
+                ft_tma_load_rows(buf0 + (size_t)s * stage_elems, &tmap, (int)(g0 / FT_ROW), &full[s]);
+            }
         }
+        return;
     }
+
+    // ---- consumer warps
     const int o0 = tid * FT_R;   // first output of this thread (tile-relative)
     for (int it = 0;; it++) {
         const int tile = blockIdx.x + it * gridDim.x;
         if (tile >= n_tiles) break;
-        const int s = it & 1;
+        const int s = it % FT_STAGES, use = it / FT_STAGES;
         int ch;
         long long tile0;
         const long long g0 = tile_origin(tile, ch, tile0);
         const int shift = (int)(g0 % FT_ROW);
         const int tile_n = (int)min((long long)FT_TILE, n_out - tile0);
-        ft_mbar_wait(&bar[s], (unsigned)((it >> 1) & 1));
+        ft_mbar_wait(&full[s], (unsigned)(use & 1));
         if (o0 < tile_n) {
             // s_x[i] = x[tile0 - H + i]
             const float2 *s_x = buf0 + (size_t)s * stage_elems + shift;
@@ -144,8 +172,7 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, float2 *__restrict__ ou
             for (; kb + FT_R <= ntaps; kb += FT_R) {
 #pragma unroll
                 for (int q = 0; q < FT_R; q++) {
-                    const float h = s_taps[kb + q];
-                    const float2 h2 = make_float2(h, h);
+                    const float2 h2 = taps.h2[kb + q];
 #pragma unroll
                     for (int r = 0; r < FT_R; r++) {
                         const int sl = (r - q + FT_R) % FT_R;
@@ -158,8 +185,7 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, float2 *__restrict__ ou
 #pragma unroll
             for (int q = 0; q < FT_R; q++) {
                 if (kb + q < ntaps) {
-                    const float h = s_taps[kb + q];
-                    const float2 h2 = make_float2(h, h);
+                    const float2 h2 = taps.h2[kb + q];
 #pragma unroll
                     for (int r = 0; r < FT_R; r++) {
                         const int sl = (r - q + FT_R) % FT_R;
@@ -173,11 +199,8 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, float2 *__restrict__ ou
             for (int r = 0; r < FT_R; r++)
                 if (o0 + r < tile_n) o[r] = acc[r];
         }
-        __syncthreads();   // every thread is done reading this stage: its buffer may be overwritten
-        if (tid == 0) {
-            const int nt = tile + FT_STAGES * gridDim.x;
-            if (nt < n_tiles) issue(nt, s);
-        }
+        __syncwarp();
+        if ((tid & 31) == 0) ft_mbar_arrive(&empty[s]);   // this warp has read everything it needs from the stage
     }
 }
 

@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBXRD_PATH = os.path.join(_HERE, "libxrd.so")
+LIBXRD_PATH = os.environ.get("XRD_LIBXRD") or os.path.join(_HERE, "libxrd.so")   # (override: kernel experiments)
 
 XRD_FLOATIQ, XRD_S16IQ, XRD_S8IQ, XRD_U8IQ, XRD_RTLU8IQ = 0, 1, 2, 3, 4
 _NP_OF_TYPE = {XRD_FLOATIQ: np.float32, XRD_S16IQ: np.int16, XRD_S8IQ: np.int8, XRD_U8IQ: np.uint8, XRD_RTLU8IQ: np.uint8}
