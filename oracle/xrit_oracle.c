@@ -810,3 +810,220 @@ void xo_diag_i8(const float *v, int64_t n, int8_t *out)
         out[i] = (int8_t)(val);
     }
 }
+
+/* ========================================================================= */
+/* Decoder front half (reference decoder/src/newdecoder.cpp:212-290)          */
+/* ========================================================================= */
+/*
+ * The decoder's first steps on the soft-symbol byte stream this path emits: sync-word correlation
+ * (:218-247), phase fix (:268-270), r = 1/2 k = 7 Viterbi (:281-290), NRZ-M for HRIT.  The classes
+ * behind those calls (SatHelper::Correlator, PacketFixer, Viterbi27 on top of libcorrect) are
+ * un-vendored like the DSP classes, so this is a restatement too -- but the reference pins the
+ * code itself: the four sync-word constants of newdecoder.cpp:21-24 are the convolutionally
+ * encoded attached sync marker 0x1ACFFC1D, and only one convention reproduces them (polynomials
+ * 0x4F then 0x6D on a register that shifts the newest bit in at the LSB, start state 0, coded bit
+ * c stored inverted, i.e. coded 0 = positive symbol; HRIT words additionally NRZ-M encoded from 0
+ * and from 1).  tests/test_decoder_oracle.py checks all four.
+ */
+#define XO_FRAMEBITS 8192
+#define XO_CODEDFRAME 16384
+#define XO_LASTBITS 64
+
+static inline int xo_parity8(unsigned v)
+{
+    v ^= v >> 4;
+    v ^= v >> 2;
+    v ^= v >> 1;
+    return (int)(v & 1);
+}
+
+/* r = 1/2, k = 7: per input bit two coded bits, poly 0x4F first, then 0x6D; sr = ((sr << 1) | bit) & 0x7F */
+void xo_conv_encode(const uint8_t *bits, int64_t n, unsigned *state, uint8_t *coded /* 2 n */)
+{
+    unsigned sr = *state & 0x7F;
+    for (int64_t i = 0; i < n; i++) {
+        sr = ((sr << 1) | (bits[i] & 1)) & 0x7F;
+        coded[2 * i] = (uint8_t)xo_parity8(sr & 0x4F);
+        coded[2 * i + 1] = (uint8_t)xo_parity8(sr & 0x6D);
+    }
+    *state = sr;
+}
+
+/* NRZ-M: out = out_prev ^ in (encode), in = out ^ out_prev (decode) */
+void xo_nrzm_encode(const uint8_t *bits, int64_t n, uint8_t *last, uint8_t *out)
+{
+    uint8_t l = *last & 1;
+    for (int64_t i = 0; i < n; i++) {
+        l ^= bits[i] & 1;
+        out[i] = l;
+    }
+    *last = l;
+}
+
+/* DifferentialEncoding::nrzmDecode on packed bytes (MSB first), newdecoder.cpp:284,289: every bit is replaced by
+ * its xor with the bit before it; the bit before the first one is 0 */
+void xo_nrzm_decode_bytes(uint8_t *data, int64_t n)
+{
+    uint8_t mask, last = 0;
+    for (int64_t i = 0; i < n; i++) {
+        mask = (uint8_t)((data[i] >> 1) & 0x7F);
+        mask |= (uint8_t)(last << 7);
+        last = data[i] & 1;
+        data[i] ^= mask;
+    }
+}
+
+/* Correlator::correlate over `length` soft bytes with the given 64-bit words (MSB = first symbol): per position the
+ * number of symbols whose hard decision agrees with the word, a byte >= 127 reading as word bit 0 and a byte < 127 as
+ * word bit 1; the first position (and, there, the first word) with the strictly highest count wins. */
+void xo_correlate(const uint8_t *data, uint32_t length, const uint64_t *words, int n_words, uint32_t *highest,
+                  uint32_t *position, uint32_t *word)
+{
+    uint32_t best = 0, bpos = 0, bword = 0;
+    if (length > 64) {
+        const uint32_t max_search = length - 64;
+        for (uint32_t i = 0; i < max_search; i++) {
+            for (int n = 0; n < n_words; n++) {
+                uint32_t c = 0;
+                for (int k = 0; k < 64; k++) {
+                    const int wbit = (int)((words[n] >> (63 - k)) & 1);
+                    const uint8_t d = data[i + k];
+                    c += (uint32_t)(((d >= 127) & (wbit == 0)) | ((d < 127) & (wbit == 1)));
+                }
+                if (c > best) {
+                    best = c;
+                    bpos = i;
+                    bword = (uint32_t)n;
+                }
+            }
+        }
+    }
+    *highest = best;
+    *position = bpos;
+    *word = bword;
+}
+
+/* PacketFixer::fixPacket(data, len, DEG_180, false): a 180 degree BPSK ambiguity inverts every soft byte */
+void xo_fix_packet_180(uint8_t *data, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++)
+        data[i] ^= 0xFF;
+}
+
+/*
+ * Viterbi27::decode: maximum-likelihood decoding of n_bits information bits from 2 n_bits soft bytes read as the
+ * reference hands them over -- raw bytes, 0 = surely coded 0 ... 255 = surely coded 1 (the int8 soft symbols of the
+ * demodulator reinterpreted as unsigned, newdecoder.cpp:215-216,281) -- with the linear metric |y - 255 c| per coded
+ * bit.  All 64 start states are equally likely (metric 0), the survivor with the smallest final metric is traced
+ * back (lowest state on ties), a state keeps the predecessor with the older bit 0 on equal metrics.  Output packed
+ * MSB first.  Returns the number of coded bits whose hard decision (byte >> 7) differs from the re-encoded output:
+ * Viterbi27::GetBER.
+ */
+int xo_viterbi27_decode(const uint8_t *soft, int n_bits, uint8_t *out_bytes)
+{
+    uint32_t *metric = (uint32_t *)malloc(sizeof(uint32_t) * 64 * 2);
+    uint64_t *dec = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n_bits);
+    uint8_t out_a[128], out_b[128];      /* coded bits of the transition into 7-bit register value r */
+    for (unsigned r = 0; r < 128; r++) {
+        out_a[r] = (uint8_t)xo_parity8(r & 0x4F);
+        out_b[r] = (uint8_t)xo_parity8(r & 0x6D);
+    }
+    uint32_t *cur = metric, *nxt = metric + 64;
+    for (int s = 0; s < 64; s++)
+        cur[s] = 0;
+    for (int t = 0; t < n_bits; t++) {
+        const int y0 = soft[2 * t], y1 = soft[2 * t + 1];
+        const uint32_t m0[2] = {(uint32_t)y0, (uint32_t)(255 - y0)};   /* |y - 255 c| for c = 0, 1 */
+        const uint32_t m1[2] = {(uint32_t)y1, (uint32_t)(255 - y1)};
+        uint64_t d = 0;
+        for (unsigned ns = 0; ns < 64; ns++) {
+            /* new state ns = ((old << 1) | bit) & 63; old is (ns >> 1) or (ns >> 1) | 32; register = (old << 1) | bit */
+            const unsigned p0 = ns >> 1, p1 = (ns >> 1) | 32;
+            const unsigned r0 = (p0 << 1) | (ns & 1), r1 = (p1 << 1) | (ns & 1);
+            const uint32_t a = cur[p0] + m0[out_a[r0]] + m1[out_b[r0]];
+            const uint32_t b = cur[p1] + m0[out_a[r1]] + m1[out_b[r1]];
+            if (a <= b) {
+                nxt[ns] = a;
+            } else {
+                nxt[ns] = b;
+                d |= 1ull << ns;
+            }
+        }
+        dec[t] = d;
+        uint32_t *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+    }
+    unsigned s = 0;
+    for (unsigned k = 1; k < 64; k++)
+        if (cur[k] < cur[s])
+            s = k;
+    memset(out_bytes, 0, (size_t)((n_bits + 7) / 8));
+    for (int t = n_bits - 1; t >= 0; t--) {
+        const unsigned bit = s & 1;
+        if (bit)
+            out_bytes[t >> 3] |= (uint8_t)(0x80 >> (t & 7));
+        s = (s >> 1) | ((unsigned)((dec[t] >> s) & 1) << 5);
+    }
+    /* re-encode from the state the trace-back ended in and count disagreements with the hard decisions */
+    unsigned sr = s << 0;   /* s now holds the 6 bits before the first decoded bit */
+    int errors = 0;
+    for (int t = 0; t < n_bits; t++) {
+        const unsigned bit = (out_bytes[t >> 3] >> (7 - (t & 7))) & 1;
+        sr = ((sr << 1) | bit) & 0x7F;
+        errors += (xo_parity8(sr & 0x4F) != (soft[2 * t] >> 7)) + (xo_parity8(sr & 0x6D) != (soft[2 * t + 1] >> 7));
+    }
+    free(metric);
+    free(dec);
+    return errors;
+}
+
+/*
+ * The loop body of newdecoder.cpp:212-300 over a buffered byte stream, without the flywheel shortcut (:222-236, which
+ * only skips work when the sync word sits where it is expected): take 16384 bytes, correlate, drop the chunk when the
+ * best correlation is below MINCORRELATIONBITS (46, :244-247), otherwise re-align on the sync word by pulling the
+ * missing bytes from the stream (:250-264), undo a 180 degree phase (LRIT only, :268-270), prepend the last 64 soft
+ * bytes of the previous frame (USE_LAST_FRAME_DATA, :273-275,296), decode, NRZ-M decode for HRIT (:283-285), drop the 4
+ * warm-up bytes (:293).  frames: 1024 bytes each; meta: 4 ints per frame {stream offset of the frame, correlation,
+ * word, Viterbi bit errors}; last_end: 64 bytes carried between calls (128s at start, :141-145).  Returns the number of
+ * frames; *consumed = bytes of the stream that are done with.
+ */
+int64_t xo_decoder_front(const uint8_t *stream, int64_t n, int lrit, uint8_t *last_end, uint8_t *frames, int32_t *meta,
+                         int64_t cap, int64_t *consumed)
+{
+    static const uint64_t HRIT_UW[2] = {0xfc4ef4fd0cc2df89ull, 0x25010b02f33d2076ull};
+    static const uint64_t LRIT_UW[2] = {0xfca2b63db00d9794ull, 0x035d49c24ff2686bull};
+    const uint64_t *words = lrit ? LRIT_UW : HRIT_UW;
+    uint8_t *vit = (uint8_t *)malloc(XO_CODEDFRAME + XO_LASTBITS);
+    uint8_t dec[(XO_FRAMEBITS + XO_LASTBITS / 2) / 8];
+    int64_t s = 0, nf = 0;
+    while (s + XO_CODEDFRAME <= n && nf < cap) {
+        uint32_t corr, pos, word;
+        xo_correlate(stream + s, XO_CODEDFRAME, words, 2, &corr, &pos, &word);
+        if (corr < 46) {
+            s += XO_CODEDFRAME;
+            continue;
+        }
+        const int64_t f = s + pos;
+        if (f + XO_CODEDFRAME > n)
+            break;   /* the rest of the frame has not arrived yet */
+        memcpy(vit, last_end, XO_LASTBITS);
+        memcpy(vit + XO_LASTBITS, stream + f, XO_CODEDFRAME);
+        if (lrit && word == 1)
+            xo_fix_packet_180(vit + XO_LASTBITS, XO_CODEDFRAME);
+        const int ber = xo_viterbi27_decode(vit, XO_FRAMEBITS + XO_LASTBITS / 2, dec);
+        if (!lrit)
+            xo_nrzm_decode_bytes(dec, sizeof dec);
+        memcpy(frames + 1024 * nf, dec + 4, 1024);
+        memcpy(last_end, vit + XO_CODEDFRAME, XO_LASTBITS);
+        meta[4 * nf] = (int32_t)f;
+        meta[4 * nf + 1] = (int32_t)corr;
+        meta[4 * nf + 2] = (int32_t)word;
+        meta[4 * nf + 3] = ber;
+        nf++;
+        s = f + XO_CODEDFRAME;
+    }
+    free(vit);
+    *consumed = s;
+    return nf;
+}

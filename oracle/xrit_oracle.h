@@ -126,6 +126,17 @@ void xo_convert_u8(const uint8_t *in, int64_t n_complex, float *out);
 float xo_rtl_alpha(uint32_t sample_rate);
 void xo_convert_rtl_u8(const uint8_t *in, int64_t n_complex, float alpha, float *avg, float *out);
 
+/* ---- decoder front half (decoder/src/newdecoder.cpp:212-290): see the comments in xrit_oracle.c ---- */
+void xo_conv_encode(const uint8_t *bits, int64_t n, unsigned *state, uint8_t *coded);
+void xo_nrzm_encode(const uint8_t *bits, int64_t n, uint8_t *last, uint8_t *out);
+void xo_nrzm_decode_bytes(uint8_t *data, int64_t n);
+void xo_correlate(const uint8_t *data, uint32_t length, const uint64_t *words, int n_words, uint32_t *highest,
+                  uint32_t *position, uint32_t *word);
+void xo_fix_packet_180(uint8_t *data, int64_t n);
+int xo_viterbi27_decode(const uint8_t *soft, int n_bits, uint8_t *out_bytes);
+int64_t xo_decoder_front(const uint8_t *stream, int64_t n, int lrit, uint8_t *last_end, uint8_t *frames, int32_t *meta,
+                         int64_t cap, int64_t *consumed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -430,13 +430,15 @@ template <class LOOP> struct SegStage {
 
     long long hist = 0;   // samples of the same stream addressable before `in` (set by run)
     bool in_s16 = false;  // this call's `in` holds S16 IQ samples (AGC as the first kernel of the chain; set by run)
+    int first_variant = 2; // kernel of this call's first pass (set by run): wn_variant, or the CTA chains of the re-runs when
+                           // the call has too few segments to fill the device with warp chains (FIFO-sized calls)
     // the fused S16 ingest exists for the default kernel shapes of the AGC only
     bool can_fuse_s16() const { return std::is_same<LOOP, AgcLoop>::value && use_wn && wn_variant == 2 && redo_variant == 4; }
     void launch(Counters &c, cudaStream_t st, bool wn, const void *in_any, float2 *out, long long n, int Ls, int Ws, int nseg,
                 int n_work, int ncp, int mode, long long in_stride, long long out_stride)
     {
         const float2 *in = static_cast<const float2 *>(in_any);
-        const int variant = (mode == 1) ? redo_variant : wn_variant;
+        const int variant = (mode == 1) ? redo_variant : first_variant;
         const unsigned char *redo_flags = (mode == 1 && chase) ? d_redo.as<unsigned char>() : (const unsigned char *)nullptr;
         if constexpr (std::is_same<LOOP, AgcLoop>::value) {
             if (in_s16) {
@@ -517,6 +519,8 @@ template <class LOOP> struct SegStage {
             const int nseg = (int)((n + Ls - 1) / Ls);
             const size_t tot = (size_t)nseg * nch;
             const int ncp = Ls / WN_CKPT + 2;
+            first_variant = wn_variant;
+            if (wn && wn_variant == 2 && redo_variant >= 3 && tot <= (size_t)2 * sm_count) first_variant = redo_variant;
             d_entry.ensure(sizeof(State) * tot);
             d_exit.ensure(sizeof(State) * tot);
             d_redo.ensure(tot);
@@ -527,7 +531,7 @@ template <class LOOP> struct SegStage {
                 // Costas: warm-ups, then put the entry states on one carrier-phase branch, then the segments.
                 // Segment 0 has no warm-up; the window kernel runs its first pre_len samples beside the others'
                 // warm-ups so that the resolution can refer to the branch the true trajectory acquires on.
-                pre_len = (wn_variant == 2 && hist == 0) ? std::min(Ws, Ls) / CPB * CPB : 0;
+                pre_len = (first_variant == 2 && hist == 0) ? std::min(Ws, Ls) / CPB * CPB : 0;
                 if (pre_len > 0) {
                     d_pre.ensure(sizeof(State) * nch);
                     d_adv0.ensure(sizeof(float) * nch);
@@ -614,6 +618,8 @@ struct MmStage {
                                     // truth), 800 k when they are full chain re-runs (which need a bitwise merge)
     long long W = 800000;           // the warm-up of the current call
     long long Lmin = 262144;
+    long long single_max = 600000;  // FIFO-sized calls (<= 512 Ki samples, Parameters.h:57) run as ONE exact chain: no
+                                    // speculation, no walks
     int nt = 0;                     // lanes per chain of mm_chain32_kernel (0 = auto)
     bool force64 = false;           // tests: always use the generic 64-bit chain kernel
     int sm_count = 148;
@@ -781,6 +787,7 @@ struct MmStage {
         if (Ls <= 0) {
             const int per_ch = std::max(1, sm_count / nch);
             Ls = std::max<long long>(Lmin, (n + per_ch - 1) / per_ch);
+            if (n <= single_max) Ls = std::max<long long>(n, 64);
         }
         const int nseg = (int)std::max<long long>(1, (n + Ls - 1) / Ls);
         const size_t tot = (size_t)nseg * nch;
@@ -1262,6 +1269,8 @@ int xrd_create(const xrd_config *cfg, xrd_demod **out)
         d->costas.use_wn = costas_wn_ok(d->costas.prm);
         d->costas.L = 4096;
         d->costas.W = 32768;
+        d->costas.chains_per_sm_max = 20;   // many channels: as many chains as the kernel's registers let an SM hold
+        d->agc.chains_per_sm_max = 24;
         CostasState c0{0.f, 0.f};
         d->costas.init(d->nch, c0);
         const float gain_omega = (cfg->clock_alpha * cfg->clock_alpha) / 4.0f;                // Parameters.h:33

@@ -556,7 +556,13 @@ __global__ void seg_verify_kernel(int nseg, typename LOOP::State *__restrict__ e
     exit_ += (size_t)ch * nseg;
     redo += (size_t)ch * nseg;
     if (mirror) mirror += (size_t)ch * nseg;
-    if (mirror && first_round) {
+    (void)first_round;
+    if (mirror) {
+        // Every round, not only the first: after a stretch without a lockable signal (dropout, burst of noise) the
+        // exact trajectory re-acquires on one of the two branches and everything the first pass did behind it may sit
+        // on the other one.  The re-run that crosses the stretch brings the true branch; from then on the relative
+        // rotation below flags ALL segments behind it at once and they are re-run in parallel from de-rotated states,
+        // instead of being discovered one per round.
         // relative rotation r_j between entry[j] and exit[j-1]; mirror[j] = xor prefix
         for (int j = threadIdx.x; j < nseg; j += blockDim.x) {
             unsigned char r = 0;
