@@ -248,6 +248,48 @@ int xrd_stage_set_loop_kernel(xrd_stage *s, int kernel);
 void xrd_stage_destroy(xrd_stage *s);
 const char *xrd_stage_last_error(const xrd_stage *s);
 
+/* ---------------------------------------------------------------------------------------
+ * Decoder front half: what decoder/src/newdecoder.cpp:212-290 does first with the soft-symbol
+ * byte stream of this path (xrd_demod_batch_i8) -- SatHelper::Correlator (:76, :218-247), frame alignment (:250-264),
+ * PacketFixer for the 180 degree ambiguity (:268-270), Viterbi27 with the last 64 soft bytes of the previous frame in
+ * front (:273-296), NRZ-M decoding for HRIT (:283-285).  Integer work, bit-exact against the oracle.  Everything
+ * behind it (de-randomiser, Reed-Solomon, channel demux) stays in the decoder.
+ * ------------------------------------------------------------------------------------- */
+typedef struct xrd_decoder_front xrd_decoder_front;
+/* lrit != 0: LRIT sync words and phase fix; else HRIT sync words and NRZ-M decoding (newdecoder.cpp:147-153).
+ * soft_mode: how the Viterbi metric reads a soft byte.  0 = raw, as the reference call chain hands it over
+ * (newdecoder.cpp:215-216,281 pass SymbolManager's int8 bytes to Viterbi27::decode untouched: the sign of every symbol
+ * is read correctly, its confidence mirrored within each half); 1 = as the signed symbol it is (+127 surest coded 0,
+ * -128 surest coded 1) -- for the case that libSatHelper converts internally, which could not be checked here. */
+#define XRD_SOFT_RAW 0
+#define XRD_SOFT_SIGNED 1
+int xrd_decoder_front_create(int device, int lrit, int soft_mode, xrd_decoder_front **out);
+void xrd_decoder_front_destroy(xrd_decoder_front *f);
+int xrd_decoder_front_reset(xrd_decoder_front *f);   /* forget the previous frame's tail (lastFrameEnd := 128) */
+
+/* == Correlator::correlate(data, length) followed by getHighestCorrelation / getHighestCorrelationPosition /
+ * getCorrelationWordNumber (newdecoder.cpp:224,238-240): the first position with the strictly highest number of hard
+ * decisions that agree with one of the two sync words (0 and 180 degrees). */
+int xrd_correlate(xrd_decoder_front *f, const uint8_t *data, uint32_t length, uint32_t *highest, uint32_t *position,
+                  uint32_t *word);
+
+typedef struct {
+    int64_t offset;        /* of the frame's first soft byte in the stream handed to the call */
+    int32_t correlation;   /* sync-word agreement, >= MINCORRELATIONBITS (46) */
+    int32_t word;          /* 0: 0 degrees, 1: 180 degrees (phaseShift, newdecoder.cpp:241) */
+    int32_t bit_errors;    /* Viterbi27::GetBER: coded bits the decoder corrected */
+    int32_t reserved;
+} xrd_frame_meta;
+
+/* The loop body of newdecoder.cpp:212-300 over a buffered stretch of the stream (`soft`: n bytes as SymbolManager sends
+ * them): chunks of 16384 bytes, dropped when the best correlation is below 46, re-aligned on the sync word otherwise;
+ * every aligned frame is phase-fixed (LRIT), Viterbi-decoded and NRZ-M decoded (HRIT) into 1024 bytes (the decoder's
+ * `vitdecData`: sync marker first).  frames_out: cap x 1024 bytes.  *consumed: bytes of the stream that are done with
+ * (feed the rest again, in front of what arrives next).  The flywheel shortcut of :222-236 -- searching only the first
+ * 1024 bytes while locked -- is a CPU economy with the same result and is not reproduced. */
+int xrd_decoder_front_run(xrd_decoder_front *f, const int8_t *soft, size_t n, uint8_t *frames_out, xrd_frame_meta *meta_out,
+                          size_t cap, size_t *n_frames, size_t *consumed);
+
 /* library / device probe: 0 if a usable sm_100 device is present */
 int xrd_device_check(int device, char *name, int name_cap, int *sm_count, int *cc_major, int *cc_minor);
 const char *xrd_version(void);

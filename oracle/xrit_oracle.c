@@ -911,15 +911,19 @@ void xo_fix_packet_180(uint8_t *data, int64_t n)
 }
 
 /*
- * Viterbi27::decode: maximum-likelihood decoding of n_bits information bits from 2 n_bits soft bytes read as the
- * reference hands them over -- raw bytes, 0 = surely coded 0 ... 255 = surely coded 1 (the int8 soft symbols of the
- * demodulator reinterpreted as unsigned, newdecoder.cpp:215-216,281) -- with the linear metric |y - 255 c| per coded
- * bit.  All 64 start states are equally likely (metric 0), the survivor with the smallest final metric is traced
- * back (lowest state on ties), a state keeps the predecessor with the older bit 0 on equal metrics.  Output packed
- * MSB first.  Returns the number of coded bits whose hard decision (byte >> 7) differs from the re-encoded output:
+ * Viterbi27::decode: maximum-likelihood decoding of n_bits information bits from 2 n_bits soft bytes with the linear
+ * metric |u - 255 c| per coded bit, u the soft byte as the decoder library reads it (0 = surely coded 0 ... 255 = surely
+ * coded 1).  soft_mode 0 (the reference call chain, literally): u is the raw byte -- newdecoder.cpp:215-216,281 hand the
+ * int8 symbols of SymbolManager to Viterbi27::decode untouched, so a weak positive symbol (+1 -> 1) counts as a surer 0
+ * than a strong one (+127 -> 127); the sign, and with it every hard decision, is right, only the confidence within each
+ * half is mirrored.  soft_mode 1: u = 127 - v for the signed symbol v (+127 -> 0, -128 -> 255), the metric a decoder fed
+ * offset-binary symbols would use -- in case libSatHelper converts internally, which could not be checked here.
+ * All 64 start states are equally likely (metric 0), the survivor with the smallest final metric is traced back
+ * (lowest state on ties), a state keeps the predecessor with the older bit 0 on equal metrics.  Output packed MSB first.
+ * Returns the number of coded bits whose hard decision (raw byte >> 7) differs from the re-encoded output:
  * Viterbi27::GetBER.
  */
-int xo_viterbi27_decode(const uint8_t *soft, int n_bits, uint8_t *out_bytes)
+int xo_viterbi27_decode(const uint8_t *soft, int n_bits, int soft_mode, uint8_t *out_bytes)
 {
     uint32_t *metric = (uint32_t *)malloc(sizeof(uint32_t) * 64 * 2);
     uint64_t *dec = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n_bits);
@@ -932,7 +936,8 @@ int xo_viterbi27_decode(const uint8_t *soft, int n_bits, uint8_t *out_bytes)
     for (int s = 0; s < 64; s++)
         cur[s] = 0;
     for (int t = 0; t < n_bits; t++) {
-        const int y0 = soft[2 * t], y1 = soft[2 * t + 1];
+        const int y0 = soft_mode ? ((127 - soft[2 * t]) & 0xFF) : soft[2 * t];
+        const int y1 = soft_mode ? ((127 - soft[2 * t + 1]) & 0xFF) : soft[2 * t + 1];
         const uint32_t m0[2] = {(uint32_t)y0, (uint32_t)(255 - y0)};   /* |y - 255 c| for c = 0, 1 */
         const uint32_t m1[2] = {(uint32_t)y1, (uint32_t)(255 - y1)};
         uint64_t d = 0;
@@ -988,8 +993,8 @@ int xo_viterbi27_decode(const uint8_t *soft, int n_bits, uint8_t *out_bytes)
  * word, Viterbi bit errors}; last_end: 64 bytes carried between calls (128s at start, :141-145).  Returns the number of
  * frames; *consumed = bytes of the stream that are done with.
  */
-int64_t xo_decoder_front(const uint8_t *stream, int64_t n, int lrit, uint8_t *last_end, uint8_t *frames, int32_t *meta,
-                         int64_t cap, int64_t *consumed)
+int64_t xo_decoder_front(const uint8_t *stream, int64_t n, int lrit, int soft_mode, uint8_t *last_end, uint8_t *frames,
+                         int32_t *meta, int64_t cap, int64_t *consumed)
 {
     static const uint64_t HRIT_UW[2] = {0xfc4ef4fd0cc2df89ull, 0x25010b02f33d2076ull};
     static const uint64_t LRIT_UW[2] = {0xfca2b63db00d9794ull, 0x035d49c24ff2686bull};
@@ -1011,7 +1016,7 @@ int64_t xo_decoder_front(const uint8_t *stream, int64_t n, int lrit, uint8_t *la
         memcpy(vit + XO_LASTBITS, stream + f, XO_CODEDFRAME);
         if (lrit && word == 1)
             xo_fix_packet_180(vit + XO_LASTBITS, XO_CODEDFRAME);
-        const int ber = xo_viterbi27_decode(vit, XO_FRAMEBITS + XO_LASTBITS / 2, dec);
+        const int ber = xo_viterbi27_decode(vit, XO_FRAMEBITS + XO_LASTBITS / 2, soft_mode, dec);
         if (!lrit)
             xo_nrzm_decode_bytes(dec, sizeof dec);
         memcpy(frames + 1024 * nf, dec + 4, 1024);

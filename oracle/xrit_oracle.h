@@ -133,9 +133,9 @@ void xo_nrzm_decode_bytes(uint8_t *data, int64_t n);
 void xo_correlate(const uint8_t *data, uint32_t length, const uint64_t *words, int n_words, uint32_t *highest,
                   uint32_t *position, uint32_t *word);
 void xo_fix_packet_180(uint8_t *data, int64_t n);
-int xo_viterbi27_decode(const uint8_t *soft, int n_bits, uint8_t *out_bytes);
-int64_t xo_decoder_front(const uint8_t *stream, int64_t n, int lrit, uint8_t *last_end, uint8_t *frames, int32_t *meta,
-                         int64_t cap, int64_t *consumed);
+int xo_viterbi27_decode(const uint8_t *soft, int n_bits, int soft_mode, uint8_t *out_bytes);
+int64_t xo_decoder_front(const uint8_t *stream, int64_t n, int lrit, int soft_mode, uint8_t *last_end, uint8_t *frames,
+                         int32_t *meta, int64_t cap, int64_t *consumed);
 
 #ifdef __cplusplus
 }

@@ -117,6 +117,17 @@ def lib():
     L.xo_convert_s16.argtypes = [vp, C.c_int64, vp]
     L.xo_convert_s8.argtypes = [vp, C.c_int64, vp]
     L.xo_diag_i8.argtypes = [vp, C.c_int64, vp]
+    up = C.POINTER(C.c_uint)
+    L.xo_conv_encode.argtypes = [vp, C.c_int64, up, vp]
+    L.xo_nrzm_encode.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint8), vp]
+    L.xo_nrzm_decode_bytes.argtypes = [vp, C.c_int64]
+    u32p = C.POINTER(C.c_uint32)
+    L.xo_correlate.argtypes = [vp, C.c_uint32, vp, C.c_int, u32p, u32p, u32p]
+    L.xo_fix_packet_180.argtypes = [vp, C.c_int64]
+    L.xo_viterbi27_decode.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.xo_viterbi27_decode.restype = C.c_int
+    L.xo_decoder_front.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    L.xo_decoder_front.restype = C.c_int64
     L.xo_convert_u8.argtypes = [vp, C.c_int64, vp]
     L.xo_rtl_alpha.argtypes = [C.c_uint32]
     L.xo_rtl_alpha.restype = C.c_float
@@ -348,3 +359,56 @@ class RtlU8:
         out = np.empty(len(x), np.float32)
         lib().xo_convert_rtl_u8(_p(x), len(x) // 2, self.alpha, C.byref(self.avg), _p(out))
         return out.view(np.complex64)
+
+
+# ---- decoder front half ----
+UW = {"lrit": (0xfca2b63db00d9794, 0x035d49c24ff2686b), "hrit": (0xfc4ef4fd0cc2df89, 0x25010b02f33d2076)}   # newdecoder.cpp:21-24
+
+
+def conv_encode(bits, state=0):
+    bits = np.ascontiguousarray(bits, np.uint8)
+    out = np.empty(2 * len(bits), np.uint8)
+    st = C.c_uint(state)
+    lib().xo_conv_encode(_p(bits), len(bits), C.byref(st), _p(out))
+    return out, st.value
+
+
+def nrzm_encode(bits, last=0):
+    bits = np.ascontiguousarray(bits, np.uint8)
+    out = np.empty(len(bits), np.uint8)
+    l = C.c_uint8(last)
+    lib().xo_nrzm_encode(_p(bits), len(bits), C.byref(l), _p(out))
+    return out, l.value
+
+
+def correlate(data, words):
+    d = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    w = np.array(words, np.uint64)
+    a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib().xo_correlate(_p(d), len(d), _p(w), len(w), C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def viterbi27(soft, n_bits, soft_mode=0):
+    s = np.ascontiguousarray(soft).view(np.uint8).reshape(-1)
+    out = np.zeros((n_bits + 7) // 8, np.uint8)
+    ber = lib().xo_viterbi27_decode(_p(s), n_bits, soft_mode, _p(out))
+    return out, ber
+
+
+class DecoderFront:
+    """xo_decoder_front with the 64 carried soft bytes"""
+
+    def __init__(self, lrit=True, soft_mode=0):
+        self.lrit, self.soft_mode = lrit, soft_mode
+        self.last_end = np.full(64, 128, np.uint8)
+
+    def run(self, soft):
+        s = np.ascontiguousarray(soft).view(np.uint8).reshape(-1)
+        cap = len(s) // 16384 + 1
+        frames = np.zeros((cap, 1024), np.uint8)
+        meta = np.zeros((cap, 4), np.int32)
+        cons = C.c_int64()
+        nf = lib().xo_decoder_front(_p(s), len(s), 1 if self.lrit else 0, self.soft_mode, _p(self.last_end), _p(frames),
+                                    _p(meta), cap, C.byref(cons))
+        return frames[:nf].copy(), meta[:nf].copy(), cons.value

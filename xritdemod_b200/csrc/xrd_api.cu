@@ -2001,3 +2001,166 @@ void xrd_stage_destroy(xrd_stage *s)
 const char *xrd_stage_last_error(const xrd_stage *) { return g_error.c_str(); }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Decoder front half: sync-word correlation, frame alignment, phase fix, Viterbi, NRZ-M
+// (reference decoder/src/newdecoder.cpp:212-290) on the soft-symbol byte stream xrd_demod_batch_i8 emits
+// ---------------------------------------------------------------------------------------
+#include "xrd_decoder.cuh"
+
+struct xrd_decoder_front {
+    int device = 0, lrit = 1, soft_mode = 0;
+    cudaStream_t stream = nullptr;
+    Counters ctr;
+    DevBuf d_soft, d_bits, d_blockmax, d_frames, d_out, d_err, d_scalars, d_last[2], d_key;
+    int cur = 0;
+    unsigned long long words[2] = {0, 0};
+    ~xrd_decoder_front()
+    {
+        if (stream) cudaStreamDestroy(stream);
+    }
+    void pack(const uint8_t *soft_dev, long long n)
+    {
+        const long long n_words = (n + 31) / 32;
+        d_bits.ensure(sizeof(unsigned) * (size_t)(n_words + 4));
+        XRD_CUDA(cudaMemsetAsync(d_bits.p, 0, sizeof(unsigned) * (size_t)(n_words + 4), stream));
+        if (n_words > 0)
+            XRD_LAUNCH(ctr, df_pack_kernel, (unsigned)((n_words + 255) / 256), 256, 0, stream, soft_dev, n, d_bits.as<unsigned>(),
+                       n_words);
+    }
+};
+
+extern "C" {
+
+int xrd_decoder_front_create(int device, int lrit, int soft_mode, xrd_decoder_front **out)
+{
+    if (!out || soft_mode < 0 || soft_mode > 1) return XRD_E_ARG;
+    *out = nullptr;
+    int rc = select_device(device);
+    if (rc) return rc;
+    xrd_decoder_front *f = new xrd_decoder_front();
+    f->device = device;
+    f->lrit = lrit ? 1 : 0;
+    f->soft_mode = soft_mode;
+    // newdecoder.cpp:21-24,147-153: the encoded sync marker for 0 and 180 degrees
+    f->words[0] = lrit ? 0xfca2b63db00d9794ull : 0xfc4ef4fd0cc2df89ull;
+    f->words[1] = lrit ? 0x035d49c24ff2686bull : 0x25010b02f33d2076ull;
+    rc = guarded([&]() {
+        XRD_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            f->d_last[i].ensure(DF_LAST);
+            XRD_CUDA(cudaMemset(f->d_last[i].p, 128, DF_LAST));   // lastFrameEnd[i] = 128, newdecoder.cpp:141-145
+        }
+        f->d_scalars.ensure(64);
+        f->d_key.ensure(sizeof(unsigned long long));
+        XRD_CUDA(cudaFuncSetAttribute(df_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)df_viterbi_smem()));
+        return (int)XRD_OK;
+    });
+    if (rc) {
+        delete f;
+        return rc;
+    }
+    *out = f;
+    return XRD_OK;
+}
+
+void xrd_decoder_front_destroy(xrd_decoder_front *f)
+{
+    if (!f) return;
+    cudaSetDevice(f->device);
+    delete f;
+}
+
+int xrd_decoder_front_reset(xrd_decoder_front *f)
+{
+    if (!f) return XRD_E_ARG;
+    return guarded([&]() {
+        XRD_CUDA(cudaSetDevice(f->device));
+        XRD_CUDA(cudaStreamSynchronize(f->stream));
+        for (int i = 0; i < 2; i++) XRD_CUDA(cudaMemset(f->d_last[i].p, 128, DF_LAST));
+        return (int)XRD_OK;
+    });
+}
+
+int xrd_correlate(xrd_decoder_front *f, const uint8_t *data, uint32_t length, uint32_t *highest, uint32_t *position,
+                  uint32_t *word)
+{
+    if (!f || (!data && length) || !highest || !position || !word) return XRD_E_ARG;
+    *highest = *position = *word = 0;
+    if (length <= 64) return XRD_OK;   // Correlator::correlate: nothing to search
+    return guarded([&]() {
+        XRD_CUDA(cudaSetDevice(f->device));
+        f->d_soft.ensure(length);
+        XRD_CUDA(cudaMemcpyAsync(f->d_soft.p, data, length, cudaMemcpyHostToDevice, f->stream));
+        f->pack(f->d_soft.as<uint8_t>(), length);
+        XRD_LAUNCH(f->ctr, df_correlate_kernel, 1, 1024, 0, f->stream, f->d_bits.as<unsigned>(), (long long)length - 64,
+                   f->words[0], f->words[1], 2, f->d_key.as<unsigned long long>());
+        unsigned long long k = 0;
+        XRD_CUDA(cudaMemcpyAsync(&k, f->d_key.p, sizeof k, cudaMemcpyDeviceToHost, f->stream));
+        XRD_CUDA(cudaStreamSynchronize(f->stream));
+        // (all counts zero: the reference reports correlation 0 at position 0 with word 0)
+        if ((k >> 41) > 0) {
+            *highest = (uint32_t)(k >> 41);
+            *position = (uint32_t)(0xFFFFFFFFFFull - ((k >> 1) & 0xFFFFFFFFFFull));
+            *word = 1u - (uint32_t)(k & 1);
+        }
+        return (int)XRD_OK;
+    });
+}
+
+int xrd_decoder_front_run(xrd_decoder_front *f, const int8_t *soft, size_t n, uint8_t *frames_out, xrd_frame_meta *meta_out,
+                          size_t cap, size_t *n_frames, size_t *consumed)
+{
+    if (!f || (!soft && n) || !n_frames || !consumed || (cap && (!frames_out || !meta_out))) return XRD_E_ARG;
+    *n_frames = 0;
+    *consumed = 0;
+    if (n < (size_t)DF_FRAME || cap == 0) return XRD_OK;
+    if (n >= (1ull << 38) || cap > 0x7fffffffull) return XRD_E_ARG;
+    return guarded([&]() {
+        XRD_CUDA(cudaSetDevice(f->device));
+        const long long N = (long long)n;
+        f->d_soft.ensure(n);
+        XRD_CUDA(cudaMemcpyAsync(f->d_soft.p, soft, n, cudaMemcpyHostToDevice, f->stream));
+        f->pack(f->d_soft.as<uint8_t>(), N);
+        const long long n_pos = N - 64;
+        const long long n_blk = (n_pos + DF_BLK - 1) / DF_BLK;
+        f->d_blockmax.ensure(sizeof(unsigned long long) * (size_t)n_blk);
+        XRD_LAUNCH(f->ctr, df_blockmax_kernel, (unsigned)n_blk, DF_BLK, 0, f->stream, f->d_bits.as<unsigned>(), n_pos, f->words[0],
+                   f->words[1], f->d_blockmax.as<unsigned long long>());
+        const int max_frames = (int)std::min<size_t>(cap, n / DF_FRAME);
+        f->d_frames.ensure(sizeof(DfFrame) * (size_t)max_frames);
+        int *d_nf = f->d_scalars.as<int>();
+        long long *d_cons = reinterpret_cast<long long *>(f->d_scalars.as<char>() + 8);
+        XRD_LAUNCH(f->ctr, df_walk_kernel, 1, 32, 0, f->stream, f->d_bits.as<unsigned>(), f->d_blockmax.as<unsigned long long>(), N,
+                   f->words[0], f->words[1], f->d_frames.as<DfFrame>(), max_frames, d_nf, d_cons);
+        int nf = 0;
+        long long cons = 0;
+        XRD_CUDA(cudaMemcpyAsync(&nf, d_nf, sizeof nf, cudaMemcpyDeviceToHost, f->stream));
+        XRD_CUDA(cudaMemcpyAsync(&cons, d_cons, sizeof cons, cudaMemcpyDeviceToHost, f->stream));
+        XRD_CUDA(cudaStreamSynchronize(f->stream));
+        *consumed = (size_t)cons;
+        if (nf <= 0) return (int)XRD_OK;
+        f->d_out.ensure((size_t)nf * (DF_BITS / 8));
+        f->d_err.ensure(sizeof(int) * (size_t)nf);
+        XRD_LAUNCH(f->ctr, df_viterbi_kernel, nf, 32, df_viterbi_smem(), f->stream, f->d_soft.as<uint8_t>(), f->d_frames.as<DfFrame>(),
+                   nf, f->lrit, f->soft_mode, f->d_last[f->cur].as<uint8_t>(), f->d_last[f->cur ^ 1].as<uint8_t>(), f->d_out.as<uint8_t>(),
+                   f->d_err.as<int>());
+        f->cur ^= 1;
+        std::vector<DfFrame> fr((size_t)nf);
+        std::vector<int> err((size_t)nf);
+        XRD_CUDA(cudaMemcpyAsync(frames_out, f->d_out.p, (size_t)nf * (DF_BITS / 8), cudaMemcpyDeviceToHost, f->stream));
+        XRD_CUDA(cudaMemcpyAsync(fr.data(), f->d_frames.p, sizeof(DfFrame) * (size_t)nf, cudaMemcpyDeviceToHost, f->stream));
+        XRD_CUDA(cudaMemcpyAsync(err.data(), f->d_err.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, f->stream));
+        XRD_CUDA(cudaStreamSynchronize(f->stream));
+        for (int i = 0; i < nf; i++) {
+            meta_out[i].offset = fr[i].offset;
+            meta_out[i].correlation = fr[i].corr;
+            meta_out[i].word = fr[i].word;
+            meta_out[i].bit_errors = err[i];
+        }
+        *n_frames = (size_t)nf;
+        return (int)XRD_OK;
+    });
+}
+
+}  // extern "C"

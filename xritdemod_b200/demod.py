@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "xrd_design_rrc", "xrd_design_lowpass", "xrd_mmse_table", "xrd_costas_gains",
     "xrd_fir_create", "xrd_agc_create", "xrd_costas_create", "xrd_clock_recovery_create", "xrd_stage_work",
     "xrd_stage_set_tuning", "xrd_stage_set_loop_kernel", "xrd_stage_destroy", "xrd_stage_last_error", "xrd_device_check", "xrd_version",
+    "xrd_decoder_front_create", "xrd_decoder_front_destroy", "xrd_decoder_front_reset", "xrd_correlate", "xrd_decoder_front_run",
 ]
 
 
@@ -66,6 +67,11 @@ class Diag(C.Structure):
         ("n_frame", C.c_int32), ("frame", C.c_int8 * 1024), ("n_symbols", C.c_uint64), ("mean_abs_i", C.c_double),
         ("mean_sq_i", C.c_double), ("mean_sq_q", C.c_double), ("snr_db", C.c_float), ("lock", C.c_float),
     ]
+
+
+class FrameMeta(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("correlation", C.c_int32), ("word", C.c_int32), ("bit_errors", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Tuning(C.Structure):
@@ -156,6 +162,14 @@ def lib():
     L.xrd_stage_destroy.restype = None
     L.xrd_stage_last_error.argtypes = [vp]
     L.xrd_stage_last_error.restype = C.c_char_p
+    L.xrd_decoder_front_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.xrd_decoder_front_destroy.argtypes = [vp]
+    L.xrd_decoder_front_destroy.restype = None
+    L.xrd_decoder_front_reset.argtypes = [vp]
+    u32p = C.POINTER(C.c_uint32)
+    L.xrd_correlate.argtypes = [vp, vp, C.c_uint32, u32p, u32p, u32p]
+    L.xrd_decoder_front_run.argtypes = [vp, vp, C.c_size_t, vp, C.POINTER(FrameMeta), C.c_size_t, C.POINTER(C.c_size_t),
+                                        C.POINTER(C.c_size_t)]
     _LIB = L
     return L
 
@@ -461,3 +475,50 @@ class Demodulator:
         out = np.empty(len(s) // 2, np.int8)
         self._check(lib().xrd_soft_i8(self._h, _p(s), len(out), _p(out)))
         return out
+
+
+class DecoderFront:
+    """The decoder's first steps on the soft-symbol byte stream (decoder/src/newdecoder.cpp:212-290): sync-word
+    correlation, frame alignment, 180-degree phase fix (LRIT), Viterbi r=1/2 k=7, NRZ-M (HRIT)."""
+
+    def __init__(self, lrit=True, soft_mode=0, device=0):
+        self._h = C.c_void_p()
+        rc = lib().xrd_decoder_front_create(device, 1 if lrit else 0, soft_mode, C.byref(self._h))
+        if rc:
+            raise XrdError(rc, lib().xrd_last_error(None).decode())
+
+    def _check(self, rc):
+        if rc < 0:
+            raise XrdError(rc, lib().xrd_last_error(None).decode())
+        return rc
+
+    def close(self):
+        if self._h:
+            lib().xrd_decoder_front_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._check(lib().xrd_decoder_front_reset(self._h))
+
+    def correlate(self, data):
+        """Correlator::correlate: (highest correlation, position, word)"""
+        d = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(lib().xrd_correlate(self._h, _p(d), len(d), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def run(self, soft):
+        """soft: int8 soft symbols; returns (frames [n, 1024] uint8, meta list of FrameMeta, consumed bytes)"""
+        d = np.ascontiguousarray(soft).view(np.int8).reshape(-1)
+        cap = len(d) // 16384 + 1
+        frames = np.zeros((cap, 1024), np.uint8)
+        meta = (FrameMeta * cap)()
+        nf, cons = C.c_size_t(), C.c_size_t()
+        self._check(lib().xrd_decoder_front_run(self._h, _p(d), len(d), _p(frames), meta, cap, C.byref(nf), C.byref(cons)))
+        return frames[: nf.value].copy(), [meta[i] for i in range(nf.value)], cons.value
