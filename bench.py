@@ -431,6 +431,18 @@ def measure(args, w, rank, local, world, devname):
         x_dev.copy_(h_in, non_blocking=True)
     torch.cuda.synchronize()
     h2d_gbs = 3 * 8.0 * n * nch / (time.perf_counter() - tc) / 1e9
+    # ... and with the step's output going the other way at the same time (two streams): one step's worth of plain
+    # copies, nothing computed -- the floor of an e2e step on this box
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    tc = time.perf_counter()
+    for _ in range(3):
+        with torch.cuda.stream(s_up):
+            x_dev.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_sym[: 2 * nsym].copy_(sym_dev[: 2 * nsym], non_blocking=True)
+    torch.cuda.synchronize()
+    copy_floor_ms = (time.perf_counter() - tc) * 1e3 / 3
     shard.barrier()
 
     if w["config"] == "c2" and not args.no_overlap:
@@ -492,7 +504,11 @@ def measure(args, w, rank, local, world, devname):
                 "one_step_at_a_time": {"value": n * nch / e2e_seq_ms / 1e3, "ms_per_step": e2e_seq_ms},
                 "h2d_ceiling": {"gbs_per_rank": [r.elapsed_ms for r in rec_h], "gbs_total": sum(r.elapsed_ms for r in rec_h),
                                 "msps_if_link_bound": sum(r.elapsed_ms for r in rec_h) / 8.0 * 1e3,
-                                "note": "plain pinned-host -> device copies of the same input on all ranks at once"},
+                                "copies_only_ms_per_step": copy_floor_ms,
+                                "copies_only_msps": n * nch / copy_floor_ms / 1e3,
+                                "note": "plain pinned-host -> device copies of the same input on all ranks at once; "
+                                        "copies_only = one step's input up and symbols down at the same time on two streams, "
+                                        "nothing computed (rank 0): what the host link allows an e2e step"},
                 "note": "xrd_demod_batch on pinned host buffers; steps_in_flight = N: consecutive steps run on N demodulator "
                         "handles (N host threads), so the PCIe copies of one step overlap the kernels of the others; every "
                         "step's H2D and D2H are inside the timed region"},

@@ -866,6 +866,23 @@ struct MmStage {
 using namespace xrd;
 
 // ---------------------------------------------------------------------------------------
+// Host -> device input copies of different demodulator handles on one device run one after the other, in
+// submission order, each at the full speed of the link, instead of side by side at a share of it: with several calls
+// in flight (one handle per host thread) the first call then starts computing while the second one
+// copies, and the link never waits for a convoy of calls that all finish copying -- and all start computing -- together.
+// ---------------------------------------------------------------------------------------
+struct H2dGate {
+    std::mutex mu;
+    cudaEvent_t last[64] = {nullptr};
+    static H2dGate &get()
+    {
+        static H2dGate g;
+        return g;
+    }
+};
+static int g_h2d_serialize = 1;
+
+// ---------------------------------------------------------------------------------------
 // the chain
 // ---------------------------------------------------------------------------------------
 static size_t type_bytes(int type)
@@ -911,6 +928,13 @@ struct xrd_demod {
     {
         if (h_pin) cudaFreeHost(h_pin);
         for (auto e : piece_ev) cudaEventDestroy(e);
+        if (h2d_done) {
+            // nobody may be left pointing at this handle's event
+            std::lock_guard<std::mutex> gate(H2dGate::get().mu);
+            for (auto &e : H2dGate::get().last)
+                if (e == h2d_done) e = nullptr;
+            cudaEventDestroy(h2d_done);
+        }
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -1114,8 +1138,21 @@ struct xrd_demod {
         int pieces = 1;
         if ((type == XRD_FLOATIQ || (type == XRD_S16IQ && agc.can_fuse_s16())) && D == 1 && nch == 1 && piece_min > 0)
             pieces = (int)std::min<long long>(max_pieces, n / piece_min);
+        if (!h2d_done) XRD_CUDA(cudaEventCreateWithFlags(&h2d_done, cudaEventDisableTiming));
+        const int dev = cfg.device_ordinal & 63;
         if (pieces <= 1) {
-            XRD_CUDA(cudaMemcpyAsync(b_raw.p, iq, sb * (size_t)n * nch, cudaMemcpyHostToDevice, stream));
+            {
+                std::unique_lock<std::mutex> gate(H2dGate::get().mu, std::defer_lock);
+                if (g_h2d_serialize) {
+                    gate.lock();
+                    if (H2dGate::get().last[dev]) XRD_CUDA(cudaStreamWaitEvent(stream, H2dGate::get().last[dev], 0));
+                }
+                XRD_CUDA(cudaMemcpyAsync(b_raw.p, iq, sb * (size_t)n * nch, cudaMemcpyHostToDevice, stream));
+                if (g_h2d_serialize) {
+                    XRD_CUDA(cudaEventRecord(h2d_done, stream));
+                    H2dGate::get().last[dev] = h2d_done;
+                }
+            }
             run_front(b_raw.p, n, 0, n, type);
             return run_back(n, sym_dev, cap, counts);
         }
@@ -1131,11 +1168,22 @@ struct xrd_demod {
         XRD_CUDA(cudaEventRecord(piece_ev[0], stream));
         XRD_CUDA(cudaStreamWaitEvent(copy_stream, piece_ev[0], 0));
         int np = 0;
-        for (long long off = 0; off < n; off += step, np++) {
-            const long long m = std::min(step, n - off);
-            XRD_CUDA(cudaMemcpyAsync((char *)b_raw.p + sb * off, (const char *)iq + sb * off, sb * (size_t)m,
-                                     cudaMemcpyHostToDevice, copy_stream));
-            XRD_CUDA(cudaEventRecord(piece_ev[np], copy_stream));
+        {
+            std::unique_lock<std::mutex> gate(H2dGate::get().mu, std::defer_lock);
+            if (g_h2d_serialize) {
+                gate.lock();
+                if (H2dGate::get().last[dev]) XRD_CUDA(cudaStreamWaitEvent(copy_stream, H2dGate::get().last[dev], 0));
+            }
+            for (long long off = 0; off < n; off += step, np++) {
+                const long long m = std::min(step, n - off);
+                XRD_CUDA(cudaMemcpyAsync((char *)b_raw.p + sb * off, (const char *)iq + sb * off, sb * (size_t)m,
+                                         cudaMemcpyHostToDevice, copy_stream));
+                XRD_CUDA(cudaEventRecord(piece_ev[np], copy_stream));
+            }
+            if (g_h2d_serialize) {
+                XRD_CUDA(cudaEventRecord(h2d_done, copy_stream));
+                H2dGate::get().last[dev] = h2d_done;
+            }
         }
         np = 0;
         for (long long off = 0; off < n; off += step, np++) {
@@ -1146,6 +1194,7 @@ struct xrd_demod {
         return run_back(n, sym_dev, cap, counts);
     }
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t h2d_done = nullptr;   // this handle's latest input copy (the next handle's copy queues behind it)
     std::vector<cudaEvent_t> piece_ev;
     long long piece_min = 16000000;   // samples; 0 disables the pieces
     int max_pieces = 2;             // more pieces shorten the Costas segments and cost more re-run rounds than the overlap wins
@@ -1225,6 +1274,7 @@ void xrd_config_defaults(xrd_config *cfg, int hrit)
 int xrd_create(const xrd_config *cfg, xrd_demod **out)
 {
     if (!cfg || !out) return XRD_E_ARG;
+    if (const char *e = getenv("XRD_H2D_SERIALIZE")) g_h2d_serialize = atoi(e);   // (measurements: 0 = copies side by side)
     *out = nullptr;
     if (cfg->n_channels < 1 || cfg->symbol_rate == 0 || cfg->sample_rate == 0 || cfg->rrc_taps < 1) {
         g_error = "bad config";
