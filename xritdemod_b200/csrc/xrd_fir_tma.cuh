@@ -48,9 +48,11 @@ __host__ __device__ inline int ft_rows(int ntaps)
     // a tile starts up to FT_ROW - 1 samples into its first row and spans FT_TILE + ntaps - 1 samples
     return (FT_ROW - 1 + FT_TILE + ntaps - 1 + FT_ROW - 1) / FT_ROW;
 }
+constexpr int FT_WTILE = 32 * FT_R;          // outputs per consumer warp and tile (2304 bytes)
 __host__ __device__ inline size_t ft_smem_bytes(int ntaps)
 {
-    return FT_HEAD + (size_t)FT_STAGES * ft_rows(ntaps) * FT_ROW * sizeof(float2);
+    // mbarriers | input ring | one output staging slab per consumer warp
+    return FT_HEAD + (size_t)FT_STAGES * ft_rows(ntaps) * FT_ROW * sizeof(float2) + (size_t)FT_WARPS * FT_WTILE * sizeof(float2);
 }
 
 __device__ __forceinline__ void ft_mbar_init(uint64_t *bar, unsigned count)
@@ -110,6 +112,7 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int rows = ft_rows(ntaps);
     const int stage_elems = rows * FT_ROW;
     float2 *buf0 = reinterpret_cast<float2 *>(ft_smem + FT_HEAD);
+    float2 *s_out = buf0 + (size_t)FT_STAGES * stage_elems;   // [FT_WARPS][FT_WTILE]: outputs on their way to HBM
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < FT_STAGES; s++) {
@@ -147,6 +150,8 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
     // ---- consumer warps
     const int o0 = tid * FT_R;   // first output of this thread (tile-relative)
+    const int lane = tid & 31, wid = tid >> 5;
+    float2 *stg = s_out + (size_t)wid * FT_WTILE;   // this warp's staging slab
     for (int it = 0;; it++) {
         const int tile = blockIdx.x + it * gridDim.x;
         if (tile >= n_tiles) break;
@@ -157,19 +162,29 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const int shift = (int)(g0 % FT_ROW);
         const int tile_n = (int)min((long long)FT_TILE, n_out - tile0);
         ft_mbar_wait(&full[s], (unsigned)(use & 1));
-        if (o0 < tile_n) {
-            // s_x[i] = x[tile0 - H + i]
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the slab's last copy has read it
+        __syncwarp();
+        float2 acc[FT_R];
+#pragma unroll
+        for (int r = 0; r < FT_R; r++) acc[r] = make_float2(0.f, 0.f);
+        {
+            // every lane computes, whether its outputs exist or not (the stage holds the samples either way; what does
+            // not exist is not stored): the loop below then sits in warp-uniform control flow and the taps stay in uniform
+            // registers.  s_x[i] = x[tile0 - H + i]
             const float2 *s_x = buf0 + (size_t)s * stage_elems + shift;
-            float2 w[FT_R], acc[FT_R];
+            float2 w[FT_R];
 #pragma unroll
             for (int r = 0; r < FT_R; r++) {
                 const int m = o0 + r;
-                w[r] = (m < tile_n) ? s_x[m + H] : make_float2(0.f, 0.f);
-                acc[r] = make_float2(0.f, 0.f);
+                w[r] = s_x[m + H];
             }
             const float2 *xb = s_x + o0 + H;   // xb[-k-1] = next sample entering the window
             int kb = 0;
-            for (; kb + FT_R <= ntaps; kb += FT_R) {
+            // (the trip count goes through a shuffle so that the compiler KNOWS it is warp-uniform: it then keeps the loop
+            // counter and the taps in uniform registers and issues FFMA2 with a uniform operand -- with three vector
+            // operands the same loop ran at 50 instead of 64 TFLOP/s)
+            const int nfull = __shfl_sync(0xffffffffu, ntaps / FT_R, 0);
+            for (int ib = 0; ib < nfull; ib++, kb += FT_R) {
 #pragma unroll
                 for (int q = 0; q < FT_R; q++) {
                     const float2 h2 = taps.h2[kb + q];
@@ -194,14 +209,38 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                     w[(FT_R - 1 - q) % FT_R] = xb[-(kb + q) - 1];
                 }
             }
-            float2 *o = out + (size_t)ch * out_ch_stride + tile0 + o0;
+            // Outputs leave through shared memory: a thread's 9 consecutive outputs are 72 bytes, so storing them
+            // directly costs 32 partial sectors per store instruction (the kernel was L1-bound on that at <= 31 taps).
+            // Staged, a full warp slab (288 outputs, 2304 contiguous bytes) goes out as ONE bulk copy issued by lane 0
+            // (cp.async.bulk shared -> global); ragged or unaligned slabs take coalesced 8-byte stores.
 #pragma unroll
-            for (int r = 0; r < FT_R; r++)
-                if (o0 + r < tile_n) o[r] = acc[r];
+            for (int r = 0; r < FT_R; r++) stg[lane * FT_R + r] = acc[r];
+        }
+        {
+            float2 *o = out + (size_t)ch * out_ch_stride + tile0 + (size_t)wid * FT_WTILE;
+            const int wn = tile_n - wid * FT_WTILE;   // outputs of this warp that exist (warp-uniform)
+            if (wn >= FT_WTILE && ((reinterpret_cast<unsigned long long>(o) & 15) == 0)) {
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(o),
+                                 "r"((unsigned)__cvta_generic_to_shared(stg)), "n"(FT_WTILE * (int)sizeof(float2))
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                }
+            } else if (wn > 0) {
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < FT_R; i++) {
+                    const int idx = lane + 32 * i;
+                    if (idx < wn) o[idx] = stg[idx];
+                }
+            }
         }
         __syncwarp();
-        if ((tid & 31) == 0) ft_mbar_arrive(&empty[s]);   // this warp has read everything it needs from the stage
+        if (lane == 0) ft_mbar_arrive(&empty[s]);   // this warp has read everything it needs from the stage
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // before the slab's memory goes away
 }
 
 // ---- host side: the tensor map of a sample buffer (cuTensorMapEncodeTiled through the runtime's driver entry point,
