@@ -293,15 +293,15 @@ struct FirStage {
     {
         const typename IN::raw *in = static_cast<const typename IN::raw *>(in_any);
         bool done = false;
-        if (poly_ok && D >= 2 && D <= 5 && !force_generic) {
+        if (poly_ok && D >= 2 && D <= 5 && !force_generic && ntaps <= FT_MAX_TAPS) {
 #define XRD_FIR_POLY(DV)                                                                                                    \
     do {                                                                                                                    \
         const size_t smem = FirPoly<DV>::smem_bytes(ntaps);                                                                 \
         if (smem > 200 * 1024) break;                                                                                       \
         XRD_CUDA(cudaFuncSetAttribute((fird_poly_kernel<DV, IN>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         dim3 grid((unsigned)((n_out + FirPoly<DV>::TILE - 1) / FirPoly<DV>::TILE), nch);                                    \
-        XRD_LAUNCH(c, (fird_poly_kernel<DV, IN>), grid, FP_THREADS, smem, st, in, hist, out, d_taps.as<float>(), ntaps,     \
-                   n_out, in_stride, out_stride);                                                                           \
+        XRD_LAUNCH(c, (fird_poly_kernel<DV, IN>), grid, FP_THREADS, smem, st, in, hist, out, tma_taps, ntaps, n_out,        \
+                   in_stride, out_stride);                                                                                  \
         done = true;                                                                                                        \
     } while (0)
             if (D == 2) XRD_FIR_POLY(2);

@@ -35,14 +35,6 @@ constexpr int FT_ROW = 128;                  // samples per tensor row (1 KB)
 #endif
 constexpr int FT_STAGES = XRD_FT_STAGES;
 constexpr int FT_HEAD = 128;                 // bytes before the first stage: the mbarriers, and slot -1 of stage 0
-constexpr int FT_MAX_TAPS = 256;
-
-// taps travel as a kernel parameter (constant bank): every FFMA2 needs its tap as an (h, h) pair, and a uniform
-// constant load delivers exactly that without a shared-memory wavefront or a register move
-struct FtTaps {
-    float2 h2[FT_MAX_TAPS];
-};
-
 __host__ __device__ inline int ft_rows(int ntaps)
 {
     // a tile starts up to FT_ROW - 1 samples into its first row and spans FT_TILE + ntaps - 1 samples

@@ -220,6 +220,13 @@ fird_kernel(const typename IN::raw *__restrict__ in, const float2 *__restrict__ 
     }
 }
 
+// Taps as a kernel parameter (constant bank), already duplicated into the (h, h) pairs FFMA2 wants: a uniform constant
+// load delivers the pair without a shared-memory wavefront or a register move, and FFMA2 takes it as a uniform operand.
+constexpr int FT_MAX_TAPS = 256;
+struct FtTaps {
+    float2 h2[FT_MAX_TAPS + 8];
+};
+
 // Decimating FIR, polyphase form: out[i] = sum_m sum_p h[m*D + p] * x_p[i - m] with x_p[i] = x[i*D - p].
 // Every phase is a stride-1 FIR, so the register sliding window of fir1_kernel applies per phase: a thread
 // owns R consecutive outputs and D windows of R samples; taps are still applied in the order k = 0..T-1
@@ -233,29 +240,27 @@ template <int D> struct FirPoly {
     __host__ __device__ static size_t smem_bytes(int ntaps)
     {
         const int M = blocks(ntaps);
-        return sizeof(float) * (size_t)((M * D + 1) & ~1) + sizeof(float2) * (size_t)D * (TILE + M);
+        return sizeof(float2) * (size_t)D * (TILE + M);
     }
 };
 
 template <int D, class IN>
 __global__ void __launch_bounds__(FP_THREADS)
 fird_poly_kernel(const typename IN::raw *__restrict__ in, const float2 *__restrict__ hist, float2 *__restrict__ out,
-                 const float *__restrict__ taps, int ntaps, long long n_out, long long in_ch_stride,
+                 const __grid_constant__ FtTaps taps, int ntaps, long long n_out, long long in_ch_stride,
                  long long out_ch_stride)
 {
     constexpr int R = FirPoly<D>::R, TILE = FirPoly<D>::TILE;
     extern __shared__ float s_mem[];
     const int M = FirPoly<D>::blocks(ntaps);
     const int XL = TILE + M;                                   // samples per phase: x_p[tile0 - M .. tile0 + TILE)
-    float *s_taps = s_mem;
-    float2 *s_xp = reinterpret_cast<float2 *>(s_mem + ((M * D + 1) & ~1));
+    float2 *s_xp = reinterpret_cast<float2 *>(s_mem);
     const int ch = blockIdx.y;
     in += (size_t)ch * in_ch_stride;
     hist += (size_t)ch * (ntaps - 1);
     out += (size_t)ch * out_ch_stride;
     const long long tile0 = (long long)blockIdx.x * TILE;
     const int tile_n = (int)min((long long)TILE, n_out - tile0);
-    for (int i = threadIdx.x; i < M * D; i += FP_THREADS) s_taps[i] = (i < ntaps) ? taps[i] : 0.f;
     // stage the contiguous input span; sample g = i'*D - p goes to phase p, slot i' - (tile0 - M)
     const long long g_lo = (tile0 - M) * D - (D - 1);
     const long long g_hi = (tile0 + tile_n - 1) * D;            // last sample any output of the tile uses
@@ -280,27 +285,46 @@ fird_poly_kernel(const typename IN::raw *__restrict__ in, const float2 *__restri
 #pragma unroll
         for (int p = 0; p < D; p++) w[p][r] = s_xp[p * XL + o0 + r + M];
     }
-    for (int mb = 0; mb < M; mb += R) {
+    // whole blocks of R tap rows (every k = m * D + p below ntaps), then the ragged rest.  The trip count goes through a
+    // shuffle so that the compiler knows it is warp-uniform and keeps counter and taps in uniform registers.
+    const int nfull = __shfl_sync(__activemask(), (ntaps / D) / R, 0);
+    int mb = 0;
+    for (int ib = 0; ib < nfull; ib++, mb += R) {
 #pragma unroll
         for (int q = 0; q < R; q++) {
             const int m = mb + q;
-            if (m < M) {
 #pragma unroll
-                for (int p = 0; p < D; p++) {
-                    const int k = m * D + p;
-                    if (k < ntaps) {
-                        const float h = s_taps[k];
+            for (int p = 0; p < D; p++) {
+                const float2 h2 = taps.h2[m * D + p];
 #pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            const int sl = (r - q + R) % R;
-                            acc[r] = __ffma2_rn(make_float2(h, h), w[p][sl], acc[r]);   // two IEEE fmaf in one FFMA2
-                        }
+                for (int r = 0; r < R; r++) {
+                    const int sl = (r - q + R) % R;
+                    acc[r] = __ffma2_rn(h2, w[p][sl], acc[r]);   // two IEEE fmaf in one FFMA2
+                }
+            }
+            // x_p[o0 - m - 1] enters the slot that x_p[o0 + R - 1 - m] leaves
+#pragma unroll
+            for (int p = 0; p < D; p++) w[p][(R - 1 - q) % R] = s_xp[p * XL + o0 - m - 1 + M];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+        const int m = mb + q;
+        if (m < M) {
+#pragma unroll
+            for (int p = 0; p < D; p++) {
+                const int k = m * D + p;
+                if (k < ntaps) {
+                    const float2 h2 = taps.h2[k];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const int sl = (r - q + R) % R;
+                        acc[r] = __ffma2_rn(h2, w[p][sl], acc[r]);
                     }
                 }
-                // x_p[o0 - m - 1] enters the slot that x_p[o0 + R - 1 - m] leaves
-#pragma unroll
-                for (int p = 0; p < D; p++) w[p][(R - 1 - q) % R] = s_xp[p * XL + o0 - m - 1 + M];
             }
+#pragma unroll
+            for (int p = 0; p < D; p++) w[p][(R - 1 - q) % R] = s_xp[p * XL + o0 - m - 1 + M];
         }
     }
 #pragma unroll
