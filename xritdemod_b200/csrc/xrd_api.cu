@@ -7,6 +7,7 @@
 #include "xrd_fir_tma.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -881,6 +882,15 @@ struct H2dGate {
     }
 };
 static int g_h2d_serialize = 1;
+// host-input calls in flight in this process (all handles): when there are others, their kernels already fill the time
+// this call's input copy takes, and cutting the copy in pieces only shortens the loop segments (measured, 4 calls in
+// flight: 22.9 ms per 125 M-sample step with one piece, 24.9 with two; one call at a time: 46.4 against 42.8)
+static std::atomic<int> g_host_calls{0};
+struct HostCallScope {
+    int others;
+    HostCallScope() : others(g_host_calls.fetch_add(1)) {}
+    ~HostCallScope() { g_host_calls.fetch_sub(1); }
+};
 
 // ---------------------------------------------------------------------------------------
 // the chain
@@ -1136,7 +1146,9 @@ struct xrd_demod {
         ensure(n);
         for (float &v : ms) v = 0.f;
         int pieces = 1;
-        if ((type == XRD_FLOATIQ || (type == XRD_S16IQ && agc.can_fuse_s16())) && D == 1 && nch == 1 && piece_min > 0)
+        HostCallScope in_flight;
+        if ((type == XRD_FLOATIQ || (type == XRD_S16IQ && agc.can_fuse_s16())) && D == 1 && nch == 1 && piece_min > 0 &&
+            (in_flight.others == 0 || pieces_forced))
             pieces = (int)std::min<long long>(max_pieces, n / piece_min);
         if (!h2d_done) XRD_CUDA(cudaEventCreateWithFlags(&h2d_done, cudaEventDisableTiming));
         const int dev = cfg.device_ordinal & 63;
@@ -1197,6 +1209,7 @@ struct xrd_demod {
     cudaEvent_t h2d_done = nullptr;   // this handle's latest input copy (the next handle's copy queues behind it)
     std::vector<cudaEvent_t> piece_ev;
     long long piece_min = 16000000;   // samples; 0 disables the pieces
+    bool pieces_forced = false;     // set_tuning(h2d_pieces): use the pieces whatever else is in flight (tests)
     int max_pieces = 2;             // more pieces shorten the Costas segments and cost more re-run rounds than the overlap wins
 };
 
@@ -1327,6 +1340,7 @@ int xrd_create(const xrd_config *cfg, xrd_demod **out)
         d->mm.init(d->nch, d->sps, gain_omega, cfg->clock_mu, cfg->clock_alpha, cfg->clock_omega_limit);  // :449
         d->n_in.assign(d->nch, 0);
         d->n_sym.assign(d->nch, 0);
+        if (const char *e = getenv("XRD_H2D_PIECES")) d->max_pieces = std::max(1, atoi(e));   // (measurements)
         d->fifo.resize(d->nch);
         for (auto &f : d->fifo) f.rtl_alpha = (float)(1.f - exp(-1.0 / (cfg->sample_rate * 0.05f)));   // RtlFrontend.cpp:57
         return (int)XRD_OK;
@@ -1775,7 +1789,10 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
     if (t->mm_rerun) d->mm.use_delta = (t->mm_rerun == 1);
     if (t->mm_walk_lanes) d->mm.delta_nt = t->mm_walk_lanes;
     if (t->mm_warm) d->mm.W_user = t->mm_warm;
-    if (t->h2d_pieces) d->max_pieces = t->h2d_pieces;
+    if (t->h2d_pieces) {
+        d->max_pieces = t->h2d_pieces;
+        d->pieces_forced = true;
+    }
     if (t->h2d_piece_min_ki) d->piece_min = (long long)t->h2d_piece_min_ki * 1024;
     return XRD_OK;
 }
