@@ -338,7 +338,7 @@ def measure(args, w, rank, local, world, devname):
     e2e_ms, in_flight, calls_timed = e2e_seq_ms, 1, ke
     if not args.no_overlap:
         gib = 8.0 * n * nch / 2 ** 30
-        nf = max(2, args.in_flight if args.in_flight else (4 if world < 4 else 2))
+        nf = max(2, args.in_flight if args.in_flight else (5 if world < 4 else 2))
         nf = max(1, min(nf, int(100 // max(gib * 5, 1e-9)) or 1))   # ~5 input-sized device buffers per handle, <= 100 GB
         more = [demod.Demodulator(mode=w["mode"], device_ordinal=local, n_channels=nch, **w["kw"]) for _ in range(nf - 1)]
         handles = [(d, h_sym)] + [(dx, torch.empty(2 * cap * nch, dtype=torch.float32).pin_memory()) for dx in more]
@@ -616,7 +616,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="e2e: one step at a time only; no extras")
     ap.add_argument("--in-flight", type=int, default=0,
-                    help="e2e: demodulator handles (host threads) in flight together (default 4; 2 from 4 GPUs up)")
+                    help="e2e: demodulator handles (host threads) in flight together (default 5; 2 from 4 GPUs up)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
