@@ -342,7 +342,7 @@ def measure(args, w, rank, local, world, devname):
         nf = max(1, min(nf, int(100 // max(gib * 5, 1e-9)) or 1))   # ~5 input-sized device buffers per handle, <= 100 GB
         more = [demod.Demodulator(mode=w["mode"], device_ordinal=local, n_channels=nch, **w["kw"]) for _ in range(nf - 1)]
         handles = [(d, h_sym)] + [(dx, torch.empty(2 * cap * nch, dtype=torch.float32).pin_memory()) for dx in more]
-        per_handle = max(1, math.ceil(args.steps / nf))
+        per_handle = max(2, math.ceil(args.steps / nf))   # at least two calls per handle: the first ones all start together
         got = [[] for _ in handles]
         api = [lib.xrd_demod_batch, h_in.data_ptr(), 0]   # entry point, input buffer, sample type
 

@@ -200,6 +200,9 @@ typedef struct {
     int32_t agc_kernel;                /* AGC first pass only, overriding loop_kernel (same values) */
     int32_t chase;                     /* 1 (default): a certified AGC/Costas re-run that has not merged at the end of
                                           its segment continues into the next one; 2: stops there (one more round) */
+    int32_t guided;                    /* 1 (default): the Costas first pass records its trajectory (the state before every
+                                          sample, 8 bytes per sample of device memory) and certified re-runs take their
+                                          proposals from it; 2: re-runs extrapolate as the first pass does */
 } xrd_tuning;
 int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t);
 

@@ -135,6 +135,25 @@ def test_loop_kernels_agree(gpu, xrd, oracle, mode, kernel):
     assert (st["costas_iters"] > 0) == (kernel >= 2)
 
 
+@pytest.mark.parametrize("guided", [1, 2])
+@pytest.mark.parametrize("rerun", [4, 7, 3])
+@pytest.mark.parametrize("seg,warm", [(16384, 2048), (65536, 16384)])
+def test_costas_reruns_guided_by_the_recorded_trajectory(gpu, xrd, oracle, guided, rerun, seg, warm):
+    """certified Costas re-runs take their proposals from the trajectory the first pass recorded (guided = 1) or
+    extrapolate (2): same symbols either way, and the record must stay usable across rounds and chased segments"""
+    _, x = make_signal("hrit", 1 << 21, channel=7)   # the slow-merging stream of C3 (carrier offset near zero)
+    ref = oracle.Chain(oracle.config(True)).process(x)
+    d = xrd.Demodulator(mode="hrit")
+    d.set_tuning(costas_seg=seg, costas_warm=warm, rerun_kernel=rerun, guided=guided)
+    check_symbols(d.demod(x), ref, "guided=%d rerun=%d seg=%d" % (guided, rerun, seg))
+    st = d.stats()
+    assert st["costas_redo"] > 0
+    # a second call on the same handle: the record of the first call is stale and must not matter
+    _, x2 = make_signal("hrit", 1 << 20, channel=2)
+    d.reset()
+    check_symbols(d.demod(x2), oracle.Chain(oracle.config(True)).process(x2), "second call, guided=%d" % guided)
+
+
 @pytest.mark.parametrize("df_hz,channel", [(0.0, 3), (-900.0, 4), (350.0, 5)])
 def test_costas_branch_resolution_over_carrier_offsets(gpu, xrd, oracle, df_hz, channel):
     """segments whose cold warm-up locks on carrier+pi are put on the true branch before they run (block phase of

@@ -376,6 +376,7 @@ template <class LOOP> struct SegStage {
     int wn_variant = 2;   // 2: one warp per chain (K = 4); 3..7: one CTA per chain, (K, warps) = (1,4) (2,4) (1,2) (2,2) (2,8)
     int redo_variant = 4; // kernel of the certified re-runs: few chains, so the widest window (fastest single chain) wins
     bool use_mirror = false;
+    bool guided = true;       // the first pass records its trajectory and the CTA-chain re-runs take their proposals from it
     bool chase = true;        // CTA-chain re-runs that do not merge inside their segment keep going into the next one
     int nch = 1, sm_count = 148;
     DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list, d_ckpt, d_iters, d_psi, d_adv, d_pre, d_adv0;
@@ -431,6 +432,7 @@ template <class LOOP> struct SegStage {
 
     long long hist = 0;   // samples of the same stream addressable before `in` (set by run)
     bool in_s16 = false;  // this call's `in` holds S16 IQ samples (AGC as the first kernel of the chain; set by run)
+    State *traj = nullptr; // this call's trajectory record (set by run; null: none, re-runs are not guided)
     int first_variant = 2; // kernel of this call's first pass (set by run): wn_variant, or the CTA chains of the re-runs when
                            // the call has too few segments to fill the device with warp chains (FIFO-sized calls)
     // the fused S16 ingest exists for the default kernel shapes of the AGC only
@@ -449,14 +451,15 @@ template <class LOOP> struct SegStage {
                     XRD_LAUNCH(c, (wn_cta_kernel<LOOP, 2, 4, InS16>), n_work, 32 * 4, 0, st, in16, out, n, Ls, Ws, nseg, n_work,
                                d_entry.template as<State>(), d_exit.template as<State>(), d_carried.template as<State>(),
                                d_list.template as<int>(), d_ckpt.template as<State>(), ncp, WN_CKPT,
-                               d_iters.template as<unsigned long long>(), prm, mode, in_stride, out_stride, hist, redo_flags);
+                               d_iters.template as<unsigned long long>(), prm, mode, in_stride, out_stride, hist, redo_flags,
+                               traj);
                 } else {
                     const int grid = (n_work + WN_WARPS - 1) / WN_WARPS;
                     XRD_LAUNCH(c, (wn_loop_kernel<LOOP, WN_K, InS16>), grid, WN_WARPS * 32, wn_smem_bytes<WN_K>(), st, in16, out, n,
                                Ls, Ws, nseg, n_work, d_entry.template as<State>(), d_exit.template as<State>(),
                                d_carried.template as<State>(), d_list.template as<int>(), d_ckpt.template as<State>(), ncp,
                                WN_CKPT, d_iters.template as<unsigned long long>(), prm, mode, in_stride, out_stride, hist,
-                               (State *)nullptr, 0);
+                               (State *)nullptr, 0, traj);
                 }
                 return;
             }
@@ -466,7 +469,7 @@ template <class LOOP> struct SegStage {
 #define XRD_WN_CTA(KV, WV)                                                                                              \
     XRD_LAUNCH(c, (wn_cta_kernel<LOOP, KV, WV>), n_work, 32 * WV, 0, st, in, out, n, Ls, Ws, nseg, n_work,              \
                d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(), d_ckpt.as<State>(), ncp, \
-               WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride, hist, redo_flags)
+               WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride, hist, redo_flags, traj)
             if (variant == 3) XRD_WN_CTA(1, 4);
             else if (variant == 4) XRD_WN_CTA(2, 4);
             else if (variant == 5) XRD_WN_CTA(1, 2);
@@ -478,7 +481,7 @@ template <class LOOP> struct SegStage {
             XRD_LAUNCH(c, (wn_loop_kernel<LOOP, WN_K>), grid, WN_WARPS * 32, wn_smem_bytes<WN_K>(), st, in, out, n, Ls, Ws, nseg,
                        n_work, d_entry.as<State>(), d_exit.as<State>(), d_carried.as<State>(), d_list.as<int>(),
                        d_ckpt.as<State>(), ncp, WN_CKPT, d_iters.as<unsigned long long>(), prm, mode, in_stride, out_stride,
-                       hist, (mode == 2 && pre_len > 0) ? d_pre.as<State>() : (State *)nullptr, pre_len);
+                       hist, (mode == 2 && pre_len > 0) ? d_pre.as<State>() : (State *)nullptr, pre_len, traj);
         } else {
             const int grid = (n_work + SEG_NTH - 1) / SEG_NTH;
             XRD_LAUNCH(c, (seg_loop_kernel<LOOP, SEG_TS>), grid, SEG_NTH, 0, st, in, out, n, Ls, Ws, nseg, n_work,
@@ -490,13 +493,15 @@ template <class LOOP> struct SegStage {
     // hist_avail: samples of the same stream that are still in place right before `in` (an earlier piece of the
     // same call); speculative warm-ups of the window kernel may start there instead of at in[0]
     // s16: `in` holds S16 IQ samples instead of cf32 (caller checked can_fuse_s16())
+    // traj_buf: trajectory record of the call, indexed like `out` (same channel stride), or null
     void run(Counters &c, cudaStream_t st, const void *in_any, float2 *out, long long n, long long in_stride,
-             long long out_stride, long long hist_avail = 0, bool s16 = false)
+             long long out_stride, long long hist_avail = 0, bool s16 = false, State *traj_buf = nullptr)
     {
         if (n <= 0) return;
         const float2 *in = static_cast<const float2 *>(in_any);
         in_s16 = s16;
         const bool wn = use_wn;
+        traj = (wn && guided) ? traj_buf : nullptr;
         hist = wn ? hist_avail : 0;
         int Ls, Ws;
         if (wn) {
@@ -920,6 +925,7 @@ struct xrd_demod {
     MmStage mm;
     // chunk buffers; per-channel stride = prefix + capacity
     DevBuf b_dec, b_agc, b_rrc, b_cos, b_sym, b_raw, b_i8;
+    DevBuf b_ctraj;            // Costas trajectory record (state before every sample), laid out like b_cos
     DevBuf d_dec_hist;         // decimator history: the last ntaps_lpf - 1 input samples of every channel, cf32 (D > 1)
     long long cap_n = 0;       // input samples per channel the buffers are sized for
     bool hist_zeroed = false;
@@ -1076,7 +1082,9 @@ struct xrd_demod {
         t_rrc.stop(stream);
         float2 *cos_out = b_cos.as<float2>() + MM_TAIL + nd_off;
         t_cos.start(stream);
-        costas.run(ctr, stream, b_rrc.as<float2>() + nd_off, cos_out, nd, nd_cap(), cos_stride(), nd_off);
+        if (costas.guided) b_ctraj.ensure(sizeof(CostasState) * (size_t)cos_stride() * nch);
+        costas.run(ctr, stream, b_rrc.as<float2>() + nd_off, cos_out, nd, nd_cap(), cos_stride(), nd_off, false,
+                   costas.guided ? b_ctraj.as<CostasState>() + MM_TAIL + nd_off : nullptr);
         t_cos.stop(stream);
         ms[0] += (D > 1) ? t_dec.ms() : 0.f;
         ms[1] += t_agc.ms();
@@ -1781,6 +1789,8 @@ int xrd_set_tuning(xrd_demod *d, const xrd_tuning *t)
         d->agc.wn_variant = t->agc_kernel;
     }
     if (t->chase) d->agc.chase = d->costas.chase = (t->chase == 1);
+    if (t->guided < 0 || t->guided > 2) return XRD_E_ARG;
+    if (t->guided) d->costas.guided = (t->guided == 1);
     if (t->costas_chains_per_sm) d->costas.chains_per_sm = t->costas_chains_per_sm;
     if (t->agc_chains_per_sm) d->agc.chains_per_sm = t->agc_chains_per_sm;
     if (t->mm_seg) d->mm.L = std::max<long long>(t->mm_seg, 64);
@@ -1859,7 +1869,7 @@ struct xrd_stage {
     SegStage<AgcLoop> agc;
     SegStage<CostasLoopK> costas;
     MmStage mm;
-    DevBuf b_in, b_out;
+    DevBuf b_in, b_out, b_traj;
     long long cap = 0;
     int prefix = 0;
     ~xrd_stage()
@@ -2003,7 +2013,9 @@ int xrd_stage_work(xrd_stage *s, const float *in, float *out, int length)
             s->agc.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_in, 0, 0);
             break;
         case xrd_stage::COSTAS:
-            s->costas.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_in, 0, 0);
+            if (s->costas.guided) s->b_traj.ensure(sizeof(CostasState) * (size_t)std::max<long long>(n_in, 1));
+            s->costas.run(s->ctr, s->stream, x, s->b_out.as<float2>(), n_in, 0, 0, 0, false,
+                          s->costas.guided ? s->b_traj.as<CostasState>() : nullptr);
             break;
         case xrd_stage::MM: {
             int64_t cnt = 0;

@@ -1445,7 +1445,7 @@ mm_delta_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, MmTra
     int wb = (int)((st.omega - omid) * MM_FIX);
     float2 P1 = st.p0, P2 = st.p1;
     bool same1 = false, same2 = false;
-    int m = 0, par = 0, iters = 0, overflow = 0;
+    int m = 0, par = 0, iters = 0, overflow = 0, fresh = 0;
     // Rings.  xf[0] = samples requested so far, xf[4] = samples every thread may read in this iteration (requested
     // five slides ago: three groups stay in flight, and a thread's wait is published by the barriers of the iteration
     // after it).  Records are requested R symbols ahead of the base, which covers the same lag (R = 8 NT).
@@ -1529,7 +1529,7 @@ mm_delta_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, MmTra
                     ai[l] = fmaf(t1, bb.y, t0 * a.y);
                 }
                 p0 = make_float2((ar[0] + ar[1]) + (ar[2] + ar[3]), (ai[0] + ai[1]) + (ai[2] + ai[3]));
-                atomicAdd(&s_fresh, 1);
+                fresh++;
             } else {
                 p0 = make_float2(0.f, 0.f);
                 if (!stopc) valid = false;
@@ -1636,6 +1636,7 @@ mm_delta_kernel(const float2 *__restrict__ in, float2 *__restrict__ stage, MmTra
         asm volatile("cp.async.wait_group 3;\n" ::: "memory");
     }
     cp_async_wait_all();
+    if (fresh) atomicAdd(&s_fresh, fresh);
     overflow = __syncthreads_or(overflow);
     if (bail) {
         if (t == 0) {

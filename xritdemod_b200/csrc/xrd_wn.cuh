@@ -29,6 +29,7 @@ namespace xrd {
 // the FP32 rate, and an inexact sum only costs an iteration) ----
 struct AgcWn {
     static constexpr int NS = 1;
+    static constexpr bool GUIDE = false;   // AGC hand-offs almost always certify at once: nothing to guide
     __device__ static __forceinline__ void widen(const AgcState &s, double *f) { f[0] = (double)s.gain; }
     __device__ static __forceinline__ AgcState narrow(const double *f)
     {
@@ -44,6 +45,7 @@ struct AgcWn {
 
 struct CostasWn {
     static constexpr int NS = 2;
+    static constexpr bool GUIDE = true;
     __device__ static __forceinline__ void widen(const CostasState &s, double *f)
     {
         f[0] = (double)s.phase;
@@ -123,8 +125,10 @@ template <class LOOP, int K, bool WRITE, int CK, class IN = InF32>
 __device__ __forceinline__ typename LOOP::State wn_run(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s_begin,
                                                        int s_end, typename LOOP::State st, const typename LOOP::Params &prm,
                                                        typename IN::raw *ring, typename LOOP::State *ck, int C, bool *merged,
-                                                       unsigned long long *iters_out)
+                                                       unsigned long long *iters_out, typename LOOP::State *__restrict__ tr = nullptr)
 {
+    // tr (optional, WRITE runs): trajectory record -- tr[i] receives the exact state before sample i, which guides the
+    // proposals of later certified re-runs of this segment (wn_run_cta)
     typedef typename LOOP::State State;
     typedef typename WnOf<LOOP>::type WN;
     constexpr int NS = WN::NS;
@@ -211,7 +215,10 @@ __device__ __forceinline__ typename LOOP::State wn_run(const typename IN::raw *_
             // ---- the run ends inside the window: flush, pick the state after the last sample
 #pragma unroll
             for (int k = 0; k < K; k++)
-                if (WRITE && lr + k < A) y[base + lr + k] = yo[k];
+                if (WRITE && lr + k < A) {
+                    y[base + lr + k] = yo[k];
+                    if (tr) tr[base + lr + k] = bs[k];
+                }
             const int ra = A - 1;
             State sel = o[0];
 #pragma unroll
@@ -228,6 +235,10 @@ __device__ __forceinline__ typename LOOP::State wn_run(const typename IN::raw *_
             if (WRITE && freed) {
 #pragma unroll
                 for (int k = 0; k < K; k++) y[base + lr + k] = yo[k];
+                if (tr) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) tr[base + lr + k] = bs[k];
+                }
             }
             const State nb = wn_shfl(o[K - 1], (tbl + Ap / K - 1) & 31);
             // checkpoint: the multiple of C in (base, base+Ap], if any (at most one: C >= NT)
@@ -348,7 +359,7 @@ wn_loop_kernel(const typename IN::raw *__restrict__ in, float2 *__restrict__ out
                const typename LOOP::State *__restrict__ carried, const int *__restrict__ list,
                typename LOOP::State *__restrict__ ckpt, int ncp, int C, unsigned long long *__restrict__ iters_total,
                typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride, long long hist,
-               typename LOOP::State *__restrict__ pre, int pre_len)
+               typename LOOP::State *__restrict__ pre, int pre_len, typename LOOP::State *__restrict__ traj)
 {
     extern __shared__ __align__(16) unsigned char wn_smem[];
     typedef typename LOOP::State State;
@@ -362,6 +373,7 @@ wn_loop_kernel(const typename IN::raw *__restrict__ in, float2 *__restrict__ out
     const int len = (int)min((long long)L, n - seg0);
     const typename IN::raw *x = in + (size_t)ch * in_ch_stride + seg0;
     float2 *y = out + (size_t)ch * out_ch_stride + seg0;
+    State *tr = traj ? traj + (size_t)ch * out_ch_stride + seg0 : nullptr;   // trajectory record, indexed like the output
     State *ck = ckpt + (size_t)g * ncp;
     unsigned long long iters = 0;
     State st;
@@ -392,12 +404,12 @@ wn_loop_kernel(const typename IN::raw *__restrict__ in, float2 *__restrict__ out
     }
     if (mode == 3) st = entry[g];
     if (mode == 0 || mode == 3) {
-        st = wn_run<LOOP, K, true, WN_CK_RECORD, IN>(x, y, 0, len, st, prm, ring, ck, C, nullptr, &iters);
+        st = wn_run<LOOP, K, true, WN_CK_RECORD, IN>(x, y, 0, len, st, prm, ring, ck, C, nullptr, &iters, tr);
         if (lane == 0) exit_[g] = st;
     } else if (mode == 1) {
         st = entry[g];
         bool merged = false;
-        st = wn_run<LOOP, K, true, WN_CK_COMPARE, IN>(x, y, 0, len, st, prm, ring, ck, C, &merged, &iters);
+        st = wn_run<LOOP, K, true, WN_CK_COMPARE, IN>(x, y, 0, len, st, prm, ring, ck, C, &merged, &iters, tr);
         if (lane == 0 && !merged) exit_[g] = st;
     }
     if (lane == 0 && iters_total) atomicAdd(iters_total, iters);
@@ -419,8 +431,10 @@ template <class LOOP, int K, int WPC, class IN = InF32> struct WnCta {
     static constexpr int NT = T * K;          // slots
     static constexpr int RS = 4 * NT;         // ring samples
     static constexpr int NS = WnOf<LOOP>::type::NS;
+    static constexpr bool GUIDE = WnOf<LOOP>::type::GUIDE;   // re-runs take their proposals from the trajectory record
     struct Shared {
         typename IN::raw ring[RS];
+        State trr[GUIDE ? RS : 1]; // ring of the trajectory record in place (guided re-runs), same indexing as `ring`
         State o[2][NT];            // literal step results of every slot
         double tot[2][WPC][NS];    // warp totals of the differences
         double bex[2][NS];         // in-warp exclusive prefix of the base thread
@@ -432,12 +446,21 @@ template <class LOOP, int K, int WPC, bool WRITE, int CK, class IN = InF32>
 __device__ __forceinline__ typename LOOP::State
 wn_run_cta(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s_begin, int s_end, typename LOOP::State st,
            const typename LOOP::Params &prm, typename WnCta<LOOP, K, WPC, IN>::Shared &sh, typename LOOP::State *ck, int C,
-           bool *merged, unsigned long long *iters_out)
+           bool *merged, unsigned long long *iters_out, typename LOOP::State *__restrict__ tr = nullptr)
 {
+    // tr (optional): trajectory record of this segment, tr[i] = state before sample i as the pass before left it.
+    // WRITE runs keep it up to date.  A re-run (CK == WN_CK_COMPARE) of a loop with WN::GUIDE also READS it: the
+    // trajectory in place started from a warm-up and is, after a short transient, the true one shifted by a few ulps
+    // (typically: same phase, frequency word a few ulps off, for tens of thousands of samples), so "record + offset at
+    // the base" is a far better proposal for the slots entering the window than a linear extrapolation -- whole
+    // windows are accepted per iteration instead of ~1/6 of one.  Acceptance stays literal, so the record only
+    // decides how far an iteration gets.
     typedef typename LOOP::State State;
     typedef typename WnOf<LOOP>::type WN;
     typedef WnCta<LOOP, K, WPC, IN> G;
     constexpr int NS = G::NS, T = G::T, NT = G::NT, RS = G::RS, MARGIN = 2 * NT;
+    constexpr bool GUIDED = G::GUIDE && CK == WN_CK_COMPARE;
+    const bool guided = GUIDED && tr != nullptr;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
 
     int base = s_begin, tbt = 0, par = 0;   // tbt: thread that holds the base slot (its slot 0)
@@ -452,20 +475,38 @@ wn_run_cta(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s
     int fill = s_begin;
     {
         const int target = min(s_begin + NT + MARGIN, s_end);
-        for (int i = fill + t; i < target; i += T) cp_async_raw(&sh.ring[i & (RS - 1)], x + i);
+        for (int i = fill + t; i < target; i += T) {
+            cp_async_raw(&sh.ring[i & (RS - 1)], x + i);
+            if (GUIDED && guided) cp_async_raw(&sh.trr[i & (G::GUIDE ? RS - 1 : 0)], tr + i);
+        }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         fill = max(fill, target);
         cp_async_wait_all();
         __syncthreads();
     }
+    double goff[NS];   // guided: exact base state minus the recorded state at the base
+#pragma unroll
+    for (int c = 0; c < NS; c++) goff[c] = 0.0;
+    if (GUIDED && guided && base < s_end) {
+        double fb[NS];
+        WN::widen(sh.trr[base & (G::GUIDE ? RS - 1 : 0)], fb);
+#pragma unroll
+        for (int c = 0; c < NS; c++) goff[c] = basew[c] - fb[c];
+    }
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const int r = t * K + k;
+        const int i = base + r;
         double f[NS];
-        WN::extrapolate(basew, r, f);
+        if (GUIDED && guided && i < s_end) {
+            WN::widen(sh.trr[i & (G::GUIDE ? RS - 1 : 0)], f);
+#pragma unroll
+            for (int c = 0; c < NS; c++) f[c] += goff[c];
+        } else {
+            WN::extrapolate(basew, r, f);
+        }
         WN::normalise(f);
         bs[k] = (r == 0) ? st : WN::narrow(f);
-        const int i = base + r;
         xs[k] = (i < s_end) ? IN::cvt(sh.ring[i & (RS - 1)]) : make_float2(0.f, 0.f);
     }
     unsigned long long iters = 0;
@@ -545,7 +586,10 @@ wn_run_cta(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s
         if (base + A >= s_end) {
 #pragma unroll
             for (int k = 0; k < K; k++)
-                if (WRITE && lr + k < A) y[base + lr + k] = yo[k];
+                if (WRITE && lr + k < A) {
+                    y[base + lr + k] = yo[k];
+                    if (tr) tr[base + lr + k] = bs[k];
+                }
             base_state = sh.o[par][(tbt * K + A - 1) & (NT - 1)];
             base += A;
             break;
@@ -556,6 +600,10 @@ wn_run_cta(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s
             if (WRITE && freed) {
 #pragma unroll
                 for (int k = 0; k < K; k++) y[base + lr + k] = yo[k];
+                if (tr) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) tr[base + lr + k] = bs[k];
+                }
             }
             const State nb = sh.o[par][(tbt * K + Ap - 1) & (NT - 1)];
             if (CK != WN_CK_NONE) {
@@ -600,6 +648,28 @@ wn_run_cta(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s
             const int i0 = base + NT + lr;
 #pragma unroll
             for (int k = 0; k < K; k++) xs[k] = (i0 + k < s_end) ? IN::cvt(sh.ring[(i0 & (RS - 1)) + k]) : make_float2(0.f, 0.f);
+            if (GUIDED && guided) {
+                // the slots that enter the window believe the record shifted by the offset measured at the new base
+                // (expressed through pb / li so that the code below is the same for both kinds of proposal)
+                double fb[NS], f0[NS];
+                WN::widen(sh.trr[(base + Ap) & (G::GUIDE ? RS - 1 : 0)], fb);
+                double nbw[NS];
+                WN::widen(base_state, nbw);
+#pragma unroll
+                for (int c = 0; c < NS; c++) goff[c] = nbw[c] - fb[c];
+                if (i0 < s_end) {
+                    WN::widen(sh.trr[i0 & (G::GUIDE ? RS - 1 : 0)], f0);
+#pragma unroll
+                    for (int c = 0; c < NS; c++) pb[c] = f0[c] + goff[c];
+#pragma unroll
+                    for (int k = 0; k < K - 1; k++) {
+                        double fk[NS];
+                        WN::widen(sh.trr[((i0 & (RS - 1)) + k + 1) & (G::GUIDE ? RS - 1 : 0)], fk);
+#pragma unroll
+                        for (int c = 0; c < NS; c++) li[k][c] = (i0 + k + 1 < s_end) ? fk[c] - f0[c] : 0.0;
+                    }
+                }
+            }
         }
         bool odd = false;
         State nbs[K];
@@ -637,7 +707,10 @@ wn_run_cta(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s
             tbt = (tbt + Ap / K) & (T - 1);
             base += Ap;
             const int target = min(base + NT + MARGIN, s_end);
-            for (int i = fill + t; i < target; i += T) cp_async_raw(&sh.ring[i & (RS - 1)], x + i);
+            for (int i = fill + t; i < target; i += T) {
+                cp_async_raw(&sh.ring[i & (RS - 1)], x + i);
+                if (GUIDED && guided) cp_async_raw(&sh.trr[i & (G::GUIDE ? RS - 1 : 0)], tr + i);
+            }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
             fill = max(fill, target);
         }
@@ -659,7 +732,7 @@ wn_cta_kernel(const typename IN::raw *__restrict__ in, float2 *__restrict__ out,
               const typename LOOP::State *__restrict__ carried, const int *__restrict__ list,
               typename LOOP::State *__restrict__ ckpt, int ncp, int C, unsigned long long *__restrict__ iters_total,
               typename LOOP::Params prm, int mode, long long in_ch_stride, long long out_ch_stride, long long hist,
-              const unsigned char *__restrict__ redo)
+              const unsigned char *__restrict__ redo, typename LOOP::State *__restrict__ traj)
 {
     typedef typename LOOP::State State;
     __shared__ __align__(16) typename WnCta<LOOP, K, WPC, IN>::Shared sh;
@@ -671,6 +744,7 @@ wn_cta_kernel(const typename IN::raw *__restrict__ in, float2 *__restrict__ out,
     const int len = (int)min((long long)L, n - seg0);
     const typename IN::raw *x = in + (size_t)ch * in_ch_stride + seg0;
     float2 *y = out + (size_t)ch * out_ch_stride + seg0;
+    State *tr = traj ? traj + (size_t)ch * out_ch_stride + seg0 : nullptr;   // trajectory record, indexed like the output
     State *ck = ckpt + (size_t)g * ncp;
     unsigned long long iters = 0;
     State st;
@@ -693,12 +767,12 @@ wn_cta_kernel(const typename IN::raw *__restrict__ in, float2 *__restrict__ out,
     }
     if (mode == 3) st = entry[g];
     if (mode == 0 || mode == 3) {
-        st = wn_run_cta<LOOP, K, WPC, true, WN_CK_RECORD, IN>(x, y, 0, len, st, prm, sh, ck, C, nullptr, &iters);
+        st = wn_run_cta<LOOP, K, WPC, true, WN_CK_RECORD, IN>(x, y, 0, len, st, prm, sh, ck, C, nullptr, &iters, tr);
         if (threadIdx.x == 0) exit_[g] = st;
     } else if (mode == 1) {
         st = entry[g];
         bool merged = false;
-        st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE, IN>(x, y, 0, len, st, prm, sh, ck, C, &merged, &iters);
+        st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE, IN>(x, y, 0, len, st, prm, sh, ck, C, &merged, &iters, tr);
         // A re-run that reaches the end of its segment without having merged holds the exact state there, so it
         // simply keeps going into the next segment -- its exit IS that segment's true entry -- until it merges with the
         // trajectory in place, as long as nobody else is re-running that segment in this round (redo flag clear: its
@@ -716,9 +790,10 @@ wn_cta_kernel(const typename IN::raw *__restrict__ in, float2 *__restrict__ out,
             jj++;
             x += L;
             y += L;
+            if (tr) tr += L;
             ck += ncp;
             const int len2 = (int)min((long long)L, n - (long long)jj * L);
-            st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE, IN>(x, y, 0, len2, st, prm, sh, ck, C, &merged, &iters);
+            st = wn_run_cta<LOOP, K, WPC, true, WN_CK_COMPARE, IN>(x, y, 0, len2, st, prm, sh, ck, C, &merged, &iters, tr);
         }
         if (threadIdx.x == 0 && !merged) exit_[gg] = st;
     }

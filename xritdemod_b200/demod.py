@@ -81,6 +81,7 @@ class Tuning(C.Structure):
         ("mm_rerun", C.c_int32), ("mm_walk_lanes", C.c_int32), ("loop_kernel", C.c_int32), ("rerun_kernel", C.c_int32),
         ("h2d_pieces", C.c_int32), ("h2d_piece_min_ki", C.c_int32), ("costas_chains_per_sm", C.c_int32),
         ("agc_chains_per_sm", C.c_int32), ("agc_kernel", C.c_int32), ("chase", C.c_int32),
+        ("guided", C.c_int32),
     ]
 
 
