@@ -154,6 +154,32 @@ def test_costas_reruns_guided_by_the_recorded_trajectory(gpu, xrd, oracle, guide
     check_symbols(d.demod(x2), oracle.Chain(oracle.config(True)).process(x2), "second call, guided=%d" % guided)
 
 
+@pytest.mark.parametrize("kernel", [2, 3, 4, 7])
+def test_checkpoint_inside_the_last_window_of_a_call(gpu, xrd, oracle, kernel):
+    """A call whose ragged last segment ends a few samples after a checkpoint position (2048 k + 1 .. + 40), on the
+    slow-merging stream so that the last segment is re-run in several rounds: the run that crosses that checkpoint in
+    its last window must leave it describing what is in place, or a later re-run 'merges' with an older run's state
+    and keeps an exit state that is a few ulps off in frequency (found with tools/exp/diff_probe*.py: the outputs of
+    the call are right, the NEXT call deviates a few thousand samples in)"""
+    _, x = make_signal("hrit", 300000, channel=7)
+    _, taps = oracle.Chain(oracle.config(True)).process(x, taps=True)
+    for cut in (170001, 170007, 170024, 163840 + 2048 + 3, 150000):
+        c = xrd.CostasLoop()
+        c.set_loop_kernel(kernel)
+        c.set_tuning(16384, 2048)
+        y = np.concatenate([c.Work(taps["rrc"][:cut]), c.Work(taps["rrc"][cut:])])
+        assert_bitexact(y, taps["costas"], "Costas kernel %d, calls cut at %d" % (kernel, cut))
+    a = xrd.AGC()
+    a.set_loop_kernel(kernel)
+    a.set_tuning(4096, 256)
+    for cut in (2048 * 40 + 5, 2048 * 41 + 17):
+        a2 = xrd.AGC()
+        a2.set_loop_kernel(kernel)
+        a2.set_tuning(4096, 256)
+        y = np.concatenate([a2.Work(x[:cut]), a2.Work(x[cut:])])
+        assert_bitexact(y, taps["agc"], "AGC kernel %d, calls cut at %d" % (kernel, cut))
+
+
 @pytest.mark.parametrize("df_hz,channel", [(0.0, 3), (-900.0, 4), (350.0, 5)])
 def test_costas_branch_resolution_over_carrier_offsets(gpu, xrd, oracle, df_hz, channel):
     """segments whose cold warm-up locks on carrier+pi are put on the true branch before they run (block phase of

@@ -225,6 +225,21 @@ __device__ __forceinline__ typename LOOP::State wn_run(const typename IN::raw *_
             for (int k = 1; k < K; k++)
                 if (k == (ra % K)) sel = o[k];
             base_state = wn_shfl(sel, (tbl + ra / K) & 31);
+            // a checkpoint inside this last window (only the ragged last segment of a call has one so close to its
+            // end) must describe what is in place now: a later re-run that found an older run's state there would
+            // declare itself merged with a trajectory this run has just overwritten
+            if (CK != WN_CK_NONE) {
+                const int i0 = (s_end - 1) & ~(C - 1);
+                if (i0 > base && i0 > 0) {
+                    const int rc = i0 - base - 1;   // rank whose literal result is the state before sample i0 (< A)
+                    State selc = o[0];
+#pragma unroll
+                    for (int k = 1; k < K; k++)
+                        if (k == (rc % K)) selc = o[k];
+                    const State cs = wn_shfl(selc, (tbl + rc / K) & 31);
+                    if (lane == 0) ck[i0 >> (31 - __clz(C))] = cs;
+                }
+            }
             base += A;
             break;
         }
@@ -327,6 +342,9 @@ __device__ __forceinline__ typename LOOP::State wn_run(const typename IN::raw *_
                 else if (lr + k == A) nbs[k] = prev[k];
             }
         }
+        // a whole window was accepted: its first slot is the new base and holds the exact state literally, not as the
+        // (telescoped or record-guided) proposal that equals it in all but pathological cases
+        if (freed && lr == 0) nbs[0] = base_state;
 #pragma unroll
         for (int k = 0; k < K; k++) bs[k] = nbs[k];
         if (Ap) {
@@ -591,6 +609,10 @@ wn_run_cta(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s
                     if (tr) tr[base + lr + k] = bs[k];
                 }
             base_state = sh.o[par][(tbt * K + A - 1) & (NT - 1)];
+            if (CK != WN_CK_NONE) {   // checkpoint inside the last window: see wn_run
+                const int i0 = (s_end - 1) & ~(C - 1);
+                if (i0 > base && i0 > 0 && t == 0) ck[i0 >> (31 - __clz(C))] = sh.o[par][(tbt * K + (i0 - base) - 1) & (NT - 1)];
+            }
             base += A;
             break;
         }
@@ -700,6 +722,9 @@ wn_run_cta(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s
                 else if (lr + k == A) nbs[k] = prev[k];
             }
         }
+        // a whole window was accepted: its first slot is the new base and holds the exact state literally, not as the
+        // (telescoped or record-guided) proposal that equals it in all but pathological cases
+        if (freed && lr == 0) nbs[0] = base_state;
 #pragma unroll
         for (int k = 0; k < K; k++) bs[k] = nbs[k];
         if (Ap) {
