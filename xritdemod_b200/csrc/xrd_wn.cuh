@@ -342,9 +342,10 @@ __device__ __forceinline__ typename LOOP::State wn_run(const typename IN::raw *_
                 else if (lr + k == A) nbs[k] = prev[k];
             }
         }
-        // a whole window was accepted: its first slot is the new base and holds the exact state literally, not as the
-        // (telescoped or record-guided) proposal that equals it in all but pathological cases
-        if (freed && lr == 0) nbs[0] = base_state;
+        // a whole window was accepted (the slide is by all NT slots): its first slot is the new base again and holds the
+        // exact state literally, not as the (telescoped or record-guided) proposal that equals it in all but
+        // pathological cases
+        if (Ap == NT && lr == 0) nbs[0] = base_state;
 #pragma unroll
         for (int k = 0; k < K; k++) bs[k] = nbs[k];
         if (Ap) {
@@ -722,9 +723,10 @@ wn_run_cta(const typename IN::raw *__restrict__ x, float2 *__restrict__ y, int s
                 else if (lr + k == A) nbs[k] = prev[k];
             }
         }
-        // a whole window was accepted: its first slot is the new base and holds the exact state literally, not as the
-        // (telescoped or record-guided) proposal that equals it in all but pathological cases
-        if (freed && lr == 0) nbs[0] = base_state;
+        // a whole window was accepted (the slide is by all NT slots): its first slot is the new base again and holds the
+        // exact state literally, not as the (telescoped or record-guided) proposal that equals it in all but
+        // pathological cases
+        if (Ap == NT && lr == 0) nbs[0] = base_state;
 #pragma unroll
         for (int k = 0; k < K; k++) bs[k] = nbs[k];
         if (Ap) {
