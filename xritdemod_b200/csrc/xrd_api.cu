@@ -349,6 +349,17 @@ __global__ void carry_prefix_kernel(float2 *buf /* start of the prefix */, int k
     for (int i = threadIdx.x; i < keep; i += blockDim.x) buf[i] = s_keep[i];
 }
 
+// Round counters go back to the host through mapped pinned memory, written by a one-thread kernel, not through the
+// copy engine: a 4-byte cudaMemcpyAsync queues behind whatever the device-to-host engine is doing, and with several
+// calls in flight that is another handle's symbol buffer (0.37 GB: 7 ms on a 55 GB/s link, 20 ms on the 19 GB/s links
+// of an 8-GPU box) -- every certified round of every stage would wait that long with its SMs idle.
+__global__ void publish_kernel(volatile int *host_dst, const int *a, const int *b)
+{
+    host_dst[0] = *a;
+    if (b) host_dst[1] = *b;
+    __threadfence_system();
+}
+
 template <class S> __global__ void take_last_kernel(S *carried, const S *exit_, int nseg, int nch)
 {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
@@ -381,7 +392,8 @@ template <class LOOP> struct SegStage {
     int nch = 1, sm_count = 148;
     DevBuf d_carried, d_entry, d_exit, d_redo, d_mirror, d_nredo, d_list, d_ckpt, d_iters, d_psi, d_adv, d_pre, d_adv0;
     int pre_len = 0;          // Costas: samples of segment 0 run ahead of the branch resolution (0: none)
-    int *h_nredo = nullptr;   // pinned
+    int *h_nredo = nullptr;   // pinned, mapped
+    int *h_nredo_dev = nullptr; // its device-side address (publish_kernel)
     uint64_t rounds = 0, redone = 0, escalations = 0;
     State s_init;
 
@@ -399,7 +411,10 @@ template <class LOOP> struct SegStage {
         d_nredo.ensure(sizeof(int));
         d_iters.ensure(sizeof(unsigned long long));
         XRD_CUDA(cudaMemset(d_iters.p, 0, sizeof(unsigned long long)));
-        if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, sizeof(int)));
+        if (!h_nredo) {
+            XRD_CUDA(cudaHostAlloc(&h_nredo, 2 * sizeof(int), cudaHostAllocMapped));
+            XRD_CUDA(cudaHostGetDevicePointer(&h_nredo_dev, h_nredo, 0));
+        }
         int dev = 0;
         XRD_CUDA(cudaGetDevice(&dev));
         XRD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -562,9 +577,9 @@ template <class LOOP> struct SegStage {
                 XRD_LAUNCH(c, (seg_verify_kernel<LOOP>), nch, 256, 0, st, nseg, d_entry.as<State>(), d_exit.as<State>(),
                            d_redo.as<unsigned char>(), use_mirror ? d_mirror.as<unsigned char>() : nullptr,
                            d_nredo.as<int>(), d_list.as<int>(), round == 0 ? 1 : 0);
-                XRD_CUDA(cudaMemcpyAsync(h_nredo, d_nredo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                XRD_LAUNCH(c, publish_kernel, 1, 1, 0, st, h_nredo_dev, d_nredo.as<int>(), (const int *)nullptr);
                 XRD_CUDA(cudaStreamSynchronize(st));
-                const int nr = *h_nredo;
+                const int nr = *(volatile int *)h_nredo;
                 if (nr == 0) break;
                 // speculation that mostly fails (weak signal: slow AGC; no lock) would need a fix-up round per
                 // segment: redo the pass with longer warm-ups and segments instead (bounded).  Re-runs of the
@@ -637,7 +652,8 @@ struct MmStage {
     bool traj_on = false;           // this call records the trajectory (more than one segment, 32-bit chain kernel)
     uint64_t bails = 0;             // delta re-runs that gave up and fell back to the chain kernel
     int ck_spacing = 65536;         // samples between chain checkpoints
-    int *h_nredo = nullptr;
+    int *h_nredo = nullptr, *h_nredo_dev = nullptr;   // pinned + mapped; [1] overflow, [2] walks that gave up, [3] stall
+                                                        // flag, [4..5] written by publish_kernel every round
     signed char *out_i8 = nullptr;  // when set, the compaction also (out != null) or only (out == null) emits int8 soft symbols
     std::vector<long long> h_offsets;
     DevBuf d_diag;                  // per-channel diagnostics of the last call (MmDiag), filled by the compaction pass
@@ -670,7 +686,11 @@ struct MmStage {
                                            // [2] a chain hit its iteration cap (non-finite samples stalled the loop)
         d_overflow.ensure(sizeof(int));
         d_diag.ensure(sizeof(MmDiag) * nch);
-        if (!h_nredo) XRD_CUDA(cudaMallocHost(&h_nredo, 4 * sizeof(int)));
+        if (!h_nredo) {
+            XRD_CUDA(cudaHostAlloc(&h_nredo, 8 * sizeof(int), cudaHostAllocMapped));
+            XRD_CUDA(cudaHostGetDevicePointer(&h_nredo_dev, h_nredo, 0));
+            memset(h_nredo, 0, 8 * sizeof(int));
+        }
         int dev = 0;
         XRD_CUDA(cudaGetDevice(&dev));
         XRD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -820,12 +840,14 @@ struct MmStage {
             dim3 vg((nseg + 127) / 128, nch);
             XRD_LAUNCH(c, mm_verify_kernel, vg, 128, 0, st, nseg, d_entry.as<MmState>(), d_exit.as<MmState>(),
                        d_redo.as<unsigned char>(), d_nredo.as<int>());
-            XRD_CUDA(cudaMemcpyAsync(h_nredo, d_nredo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            XRD_CUDA(cudaMemcpyAsync(h_nredo + 3, d_nredo.as<int>() + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+            // [4] segments flagged, [5] a chain stalled -- through mapped memory, see publish_kernel
+            XRD_LAUNCH(c, publish_kernel, 1, 1, 0, st, h_nredo_dev + 4, d_nredo.as<int>(), d_nredo.as<int>() + 2);
             XRD_CUDA(cudaStreamSynchronize(st));
-            if (*h_nredo == 0 || h_nredo[3]) break;   // closed, or a chain stalled (reported as overflow below)
+            const int nr = ((volatile int *)h_nredo)[4], stalled_now = ((volatile int *)h_nredo)[5];
+            h_nredo[3] = stalled_now;
+            if (nr == 0 || stalled_now) break;   // closed, or a chain stalled (reported as overflow below)
             rounds++;
-            redone += (uint64_t)*h_nredo;
+            redone += (uint64_t)nr;
             // the delta kernel clears the flag of every segment it finishes; the chain kernel takes what is left
             if (traj_on) launch_delta(c, st, grid, in, n, Ls, nseg, cap_seg, in_stride, stage_stride);
             launch_chain(c, st, grid, in, n, Ls, nseg, cap_seg, 1, in_stride, stage_stride);
