@@ -453,6 +453,7 @@ def measure(args, w, rank, local, world, devname):
     recs = shard.gather_records(rec)
     rec_e = shard.gather_records(shard.StreamRecord(rank, nch, n * nch, nsym, e2e_ms, checksum))
     rec_h = shard.gather_records(shard.StreamRecord(rank, nch, 0, 0, h2d_gbs, 0))
+    rec_f = shard.gather_records(shard.StreamRecord(rank, nch, 0, 0, copy_floor_ms, 0))
     if rank != 0:
         return None
     agg, agg_e = shard.aggregate(recs), shard.aggregate(rec_e)
@@ -504,11 +505,13 @@ def measure(args, w, rank, local, world, devname):
                 "one_step_at_a_time": {"value": n * nch / e2e_seq_ms / 1e3, "ms_per_step": e2e_seq_ms},
                 "h2d_ceiling": {"gbs_per_rank": [r.elapsed_ms for r in rec_h], "gbs_total": sum(r.elapsed_ms for r in rec_h),
                                 "msps_if_link_bound": sum(r.elapsed_ms for r in rec_h) / 8.0 * 1e3,
-                                "copies_only_ms_per_step": copy_floor_ms,
-                                "copies_only_msps": n * nch / copy_floor_ms / 1e3,
+                                "copies_only_ms_per_step": max(r.elapsed_ms for r in rec_f),
+                                "copies_only_ms_per_rank": [r.elapsed_ms for r in rec_f],
+                                "copies_only_msps": world * n * nch / max(r.elapsed_ms for r in rec_f) / 1e3,
                                 "note": "plain pinned-host -> device copies of the same input on all ranks at once; "
                                         "copies_only = one step's input up and symbols down at the same time on two streams, "
-                                        "nothing computed (rank 0): what the host link allows an e2e step"},
+                                        "nothing computed, all ranks at once, slowest rank: what the host links of this box "
+                                        "allow an e2e step (copies_only_msps is the ceiling of e2e.value)"},
                 "note": "xrd_demod_batch on pinned host buffers; steps_in_flight = N: consecutive steps run on N demodulator "
                         "handles (N host threads), so the PCIe copies of one step overlap the kernels of the others; every "
                         "step's H2D and D2H are inside the timed region"},
