@@ -3,6 +3,8 @@ kernels treat specially: checkpoints every 2048 samples, segment ends, the 16-sa
 kernel shapes and re-run strategies, on the eight C3 streams, against the oracle demodulating the same stream in one
 piece.  The demodulated symbols must not depend on any of it, bit for bit.  (A sibling of the script that found the
 stale-checkpoint bug of round 2, profiles/r02_compute_sanitizer.md.)"""
+import os
+
 import numpy as np
 import pytest
 
@@ -10,6 +12,7 @@ from conftest import assert_bitexact, make_signal
 
 pytestmark = pytest.mark.gpu
 N = 600000
+SEEDS = int(os.environ.get("XRD_FUZZ_SEEDS", "12"))   # a longer campaign: XRD_FUZZ_SEEDS=300 pytest tests/test_gpu_fuzz.py
 SPECIAL = (2048, 4096, 8192, 16384, 32768, 65536, 60000, 100000)
 
 
@@ -55,7 +58,7 @@ def _tuning(rng):
     return t
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(SEEDS))
 def test_random_call_boundaries_and_tunings(gpu, xrd, oracle, siggen, seed):
     rng = np.random.default_rng(1000 + seed)
     for case in range(6):
@@ -81,7 +84,7 @@ def test_random_call_boundaries_and_tunings(gpu, xrd, oracle, siggen, seed):
             seed, case, mode, channel, s16, cuts[1:-1], tune))
 
 
-@pytest.mark.parametrize("seed", range(3))
+@pytest.mark.parametrize("seed", range(max(3, SEEDS // 4)))
 def test_random_multi_channel_batches(gpu, xrd, oracle, seed):
     """several channels per call (configs[4] shape), ragged calls: every channel equals its own one-piece oracle run"""
     rng = np.random.default_rng(3000 + seed)
@@ -102,7 +105,7 @@ def test_random_multi_channel_batches(gpu, xrd, oracle, seed):
                 seed, case, c, nch, cuts[1:-1], tune))
 
 
-@pytest.mark.parametrize("seed", range(3))
+@pytest.mark.parametrize("seed", range(max(3, SEEDS // 4)))
 def test_random_ragged_stage_calls(gpu, xrd, oracle, seed):
     """the same for the three loop operators on their own (SatHelper seam: Work(in, out, n) with any n)"""
     rng = np.random.default_rng(2000 + seed)
