@@ -6,12 +6,13 @@
 //
 //   * every slot of a ring of NT consecutive samples holds a BELIEVED state for its sample;
 //   * each iteration all slots apply the literal step to their believed state: o = F(s, x);
-//   * the state differences o - s are taken exactly (fixed point, int64) and prefix-summed in
+//   * the state differences o - s are taken exactly (FP64 differences of FP32 states) and prefix-summed in
 //     sample order from the exact state of the base sample; the sums are the next believed states
 //     (if every believed state up to a slot was true, the sum telescopes to the true state of the
 //     next slot exactly -- the truth is a fixed point of this map, and because F contracts and FP32
 //     rounding snaps nearby states together, the iteration converges to it from a linear
-//     extrapolation in a handful of rounds, ~25 samples per round at NT = 128);
+//     extrapolation in a handful of rounds, ~30 samples per round at NT = 128; a certified re-run
+//     starts from the trajectory the pass before recorded instead, see wn_run_cta);
 //   * acceptance is literal: slot r is exact iff slot r-1 is exact and believed[r] == o[r-1]
 //     bit for bit.  The leading exact run of A >= 1 samples is emitted, the base moves to sample A
 //     with the literal state o[A-1], and the freed slots re-enter at the far end of the window.
