@@ -13,6 +13,7 @@ from conftest import assert_bitexact, make_signal
 pytestmark = pytest.mark.gpu
 N = 600000
 SEEDS = int(os.environ.get("XRD_FUZZ_SEEDS", "12"))   # a longer campaign: XRD_FUZZ_SEEDS=300 pytest tests/test_gpu_fuzz.py
+BASE = int(os.environ.get("XRD_FUZZ_BASE", "0"))      # ... on other seeds: XRD_FUZZ_BASE=100000
 SPECIAL = (2048, 4096, 8192, 16384, 32768, 65536, 60000, 100000)
 
 
@@ -60,7 +61,7 @@ def _tuning(rng):
 
 @pytest.mark.parametrize("seed", range(SEEDS))
 def test_random_call_boundaries_and_tunings(gpu, xrd, oracle, siggen, seed):
-    rng = np.random.default_rng(1000 + seed)
+    rng = np.random.default_rng(BASE + 1000 + seed)
     for case in range(6):
         mode = "hrit" if rng.random() < 0.7 else "lrit"
         channel = int(rng.integers(0, 8))
@@ -87,7 +88,7 @@ def test_random_call_boundaries_and_tunings(gpu, xrd, oracle, siggen, seed):
 @pytest.mark.parametrize("seed", range(max(3, SEEDS // 4)))
 def test_random_multi_channel_batches(gpu, xrd, oracle, seed):
     """several channels per call (configs[4] shape), ragged calls: every channel equals its own one-piece oracle run"""
-    rng = np.random.default_rng(3000 + seed)
+    rng = np.random.default_rng(BASE + 3000 + seed)
     nch = int(rng.integers(2, 6))
     n = 300000
     xs = np.stack([make_signal("lrit", n, channel=c)[1] for c in range(nch)])
@@ -108,7 +109,7 @@ def test_random_multi_channel_batches(gpu, xrd, oracle, seed):
 @pytest.mark.parametrize("seed", range(max(3, SEEDS // 4)))
 def test_random_ragged_stage_calls(gpu, xrd, oracle, seed):
     """the same for the three loop operators on their own (SatHelper seam: Work(in, out, n) with any n)"""
-    rng = np.random.default_rng(2000 + seed)
+    rng = np.random.default_rng(BASE + 2000 + seed)
     channel = int(rng.integers(0, 8))
     _, x = make_signal("hrit", N, channel=channel)
     ch = oracle.Chain(oracle.config(True))
