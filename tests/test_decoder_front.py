@@ -77,6 +77,35 @@ def test_viterbi_inverts_the_encoder_through_noise(oracle):
     assert np.array_equal(np.unpackbits(out)[: len(bits) - 40], bits[:-40])
 
 
+@pytest.mark.parametrize("soft_mode", [0, 1])
+def test_viterbi_is_maximum_likelihood_by_brute_force(oracle, soft_mode):
+    """for short blocks every (start state, bit sequence) can be enumerated: the decoder's output must have the
+    smallest total metric sum |u - 255 c| of all 64 x 2^n candidates (an independent statement of what the
+    add-compare-select recursion computes; numpy, not the oracle's code)"""
+    n = 10
+    rng = np.random.default_rng(77 + soft_mode)
+    parity = np.array([bin(i).count("1") & 1 for i in range(128)], dtype=np.int64)
+    starts = np.arange(64, dtype=np.int64)[:, None]
+    seqs = np.arange(1 << n, dtype=np.int64)[None, :]
+    for trial in range(6):
+        soft = rng.integers(-128, 128, 2 * n).astype(np.int8)
+        if trial == 0:
+            soft[:] = 0          # all ties
+        u = ((127 - soft.astype(np.int64)) & 0xFF) if soft_mode else soft.view(np.uint8).astype(np.int64)
+        sr = np.broadcast_to(starts, (64, 1 << n)).copy()
+        total = np.zeros((64, 1 << n), np.int64)
+        for t in range(n):
+            bit = (seqs >> (n - 1 - t)) & 1
+            sr = ((sr << 1) | bit) & 0x7F
+            ca, cb = parity[sr & 0x4F], parity[sr & 0x6D]
+            total += np.abs(u[2 * t] - 255 * ca) + np.abs(u[2 * t + 1] - 255 * cb)
+        best = int(total.min())
+        out, _ = oracle.viterbi27(soft, n, soft_mode=soft_mode)
+        got = int("".join(str(int(b)) for b in np.unpackbits(out)[:n]), 2)
+        assert int(total[:, got].min()) == best, "trial %d: decoded sequence has metric %d, the best is %d" % (
+            trial, int(total[:, got].min()), best)
+
+
 def test_correlator_finds_planted_words(oracle):
     rng = np.random.default_rng(2)
     data = np.clip(np.rint(rng.normal(0, 40, 16384)), -128, 127).astype(np.int8)
